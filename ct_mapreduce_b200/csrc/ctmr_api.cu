@@ -1,0 +1,602 @@
+// ctmr_api.cu -- the C ABI of include/ctmr.h: context, issuer registry, host-buffer batch
+// pipeline (H2D / kernels / D2H overlapped over three streams) and the device-resident entry points.
+// There is deliberately no CPU implementation of the path in this file or anywhere in the library:
+// without a CUDA device ctmr_create fails.
+#include <array>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ctmr_kernels.cuh"
+
+using namespace ctmr;
+
+namespace {
+
+constexpr int kStages = 3;                      // host-API pipeline depth
+constexpr uint64_t kStageEntries = 1ull << 18;  // entries per pipeline stage
+constexpr uint64_t kStageBytes = 768ull << 20;  // leaf bytes per pipeline stage
+
+thread_local std::string g_create_error;
+
+struct Stage {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t reduced = nullptr;  // recorded after this stage's resolve kernel
+    uint8_t* blob = nullptr;
+    uint64_t* offsets = nullptr;
+    uint32_t* issuer_idx = nullptr;
+    uint8_t* status = nullptr;
+    uint8_t* sha = nullptr;
+    int64_t* exp_hour = nullptr;
+    uint32_t* serial_off = nullptr;
+    uint32_t* serial_len = nullptr;
+    uint8_t* was_unknown = nullptr;
+    uint8_t* first = nullptr;
+    ctmr_key* keys = nullptr;
+    uint32_t* slot_of = nullptr;
+    uint32_t* pair_slot = nullptr;
+};
+
+}  // namespace
+
+struct ctmr_ctx {
+    int device = 0;
+    int sm_count = 148;
+    uint32_t flags = 0;
+    cudaStream_t stream = nullptr;
+    DeviceState st{};
+    FilterCfg filter{};
+    uint64_t next_index = 0;
+    uint64_t stage_entries = 0, stage_bytes = 0;
+    bool stages_ready = false;
+    Stage stages[kStages];
+    // issuer registry (Issuer.ID digests, storage/types.go:124-130)
+    std::unordered_map<std::string, uint32_t> issuer_by_der;
+    std::unordered_map<std::string, uint32_t> issuer_by_digest;
+    std::vector<std::array<uint8_t, 32>> digests;
+    uint32_t* issuer_map_dev = nullptr;
+    uint32_t issuer_map_cap = 0;
+    // scratch of the device-resident entry points
+    ctmr_key* keys_scratch = nullptr;
+    uint32_t* slot_scratch = nullptr;
+    uint32_t* pair_scratch = nullptr;
+    uint8_t* bits_scratch = nullptr;
+    uint64_t scratch_cap = 0;
+    unsigned long long* small_dev = nullptr;  // [64] cursors / cardinality result
+    std::string err;
+};
+
+namespace {
+
+int fail(ctmr_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            return fail((ctx), e_ == cudaErrorMemoryAllocation ? CTMR_E_NOMEM : CTMR_E_CUDA,             \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                            \
+        }                                                                                               \
+    } while (0)
+
+uint64_t pow2_at_least(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// strings.Split(*ctconfig.IssuerCNFilter, ",") -- no trimming (ct-fetch.go:58)
+int build_filter(const ctmr_config* cfg, FilterCfg& f) {
+    std::memset(&f, 0, sizeof f);
+    f.filter_nonempty = cfg->issuer_cn_filter_len != 0;
+    f.log_expired = cfg->log_expired_entries != 0;
+    f.flags = cfg->flags;
+    if (!f.filter_nonempty) return 0;
+    if (cfg->issuer_cn_filter_len > sizeof f.bytes) return -1;
+    uint32_t start = 0, np = 0, used = 0;
+    for (uint32_t i = 0; i <= cfg->issuer_cn_filter_len; ++i) {
+        if (i == cfg->issuer_cn_filter_len || cfg->issuer_cn_filter[i] == ',') {
+            if (np >= 32) return -1;
+            f.off[np] = (uint16_t)used;
+            std::memcpy(f.bytes + used, cfg->issuer_cn_filter + start, i - start);
+            used += i - start;
+            ++np;
+            f.off[np] = (uint16_t)used;
+            start = i + 1;
+        }
+    }
+    f.n_prefix = np;
+    return 0;
+}
+
+int ensure_stages(ctmr_ctx* c) {
+    if (c->stages_ready) return CTMR_OK;
+    for (int k = 0; k < kStages; ++k) {
+        Stage& s = c->stages[k];
+        const uint64_t E = c->stage_entries;
+        CU(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&s.reduced, cudaEventDisableTiming));
+        CU(c, cudaMalloc(&s.blob, c->stage_bytes + 64));
+        CU(c, cudaMalloc(&s.offsets, (E + 1) * sizeof(uint64_t)));
+        CU(c, cudaMalloc(&s.issuer_idx, E * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.status, E));
+        CU(c, cudaMalloc(&s.sha, E * 32));
+        CU(c, cudaMalloc(&s.exp_hour, E * sizeof(int64_t)));
+        CU(c, cudaMalloc(&s.serial_off, E * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.serial_len, E * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.was_unknown, E));
+        CU(c, cudaMalloc(&s.first, E));
+        CU(c, cudaMalloc(&s.keys, E * sizeof(ctmr_key)));
+        CU(c, cudaMalloc(&s.slot_of, E * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.pair_slot, E * sizeof(uint32_t)));
+    }
+    c->stages_ready = true;
+    return CTMR_OK;
+}
+
+int ensure_scratch(ctmr_ctx* c, uint64_t n) {
+    if (n <= c->scratch_cap) return CTMR_OK;
+    CU(c, cudaDeviceSynchronize());
+    cudaFree(c->keys_scratch); cudaFree(c->slot_scratch); cudaFree(c->pair_scratch); cudaFree(c->bits_scratch);
+    c->keys_scratch = nullptr; c->slot_scratch = c->pair_scratch = nullptr; c->bits_scratch = nullptr;
+    c->scratch_cap = 0;
+    CU(c, cudaMalloc(&c->keys_scratch, n * sizeof(ctmr_key)));
+    CU(c, cudaMalloc(&c->slot_scratch, n * sizeof(uint32_t)));
+    CU(c, cudaMalloc(&c->pair_scratch, n * sizeof(uint32_t)));
+    CU(c, cudaMalloc(&c->bits_scratch, 2 * n));
+    c->scratch_cap = n;
+    return CTMR_OK;
+}
+
+void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, MapParams& p) {
+    std::memset(&p, 0, sizeof p);
+    p.blob = b->blob;
+    p.blob_bytes = b->blob_bytes;
+    p.offsets = b->offsets;
+    p.n = b->n;
+    p.issuer_idx = b->issuer_idx;
+    p.issuer_map = b->issuer_map;
+    p.issuer_map_len = b->issuer_map_len;
+    p.first_index = b->first_index;
+    // NotAfter.Before(now): split now into whole seconds and "has a fractional part"
+    int64_t ns = b->now_unix_ns;
+    int64_t sec = ns >= 0 ? ns / 1000000000LL : -((-ns + 999999999LL) / 1000000000LL);
+    p.now_sec = sec;
+    p.now_frac_nonzero = (ns - sec * 1000000000LL) != 0;
+    p.status = o->status;
+    p.sha256 = (c->flags & CTMR_F_NO_FINGERPRINT) ? nullptr : o->sha256;
+    p.exp_hour = o->exp_hour;
+    p.serial_off = o->serial_off;
+    p.serial_len = o->serial_len;
+    p.keys = o->keys;
+    p.status_counts = c->st.status_counts;
+    p.filter = c->filter;
+}
+
+int reduce_on(ctmr_ctx* c, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, uint32_t* pair_slot, uint8_t* was_unknown,
+              uint8_t* first, cudaStream_t s) {
+    CU(c, launch_insert(c->st, keys, m, slot_of, s));
+    CU(c, launch_resolve(c->st, keys, m, slot_of, pair_slot, was_unknown, s));
+    CU(c, launch_resolve_pairs(c->st, keys, m, pair_slot, was_unknown, first, s));
+    return CTMR_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+uint32_t ctmr_abi_version(void) { return CTMR_ABI_VERSION; }
+
+const char* ctmr_last_error(ctmr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void* ctmr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void ctmr_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int ctmr_create(const ctmr_config* cfg, ctmr_ctx** out) {
+    if (!cfg || !out || cfg->struct_size < sizeof(ctmr_config)) return fail(nullptr, CTMR_E_INVALID, "bad config");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+        (void)cudaGetLastError();
+        return fail(nullptr, CTMR_E_NO_DEVICE, "no usable CUDA device (libctmr has no CPU fallback)");
+    }
+    ctmr_ctx* c = new (std::nothrow) ctmr_ctx();
+    if (!c) return fail(nullptr, CTMR_E_NOMEM, "host allocation failed");
+    auto bail = [&](int code) {
+        g_create_error = c->err;
+        ctmr_destroy(c);
+        return code;
+    };
+    c->device = cfg->device;
+    c->flags = cfg->flags;
+    if (build_filter(cfg, c->filter)) {
+        c->err = "issuerCNFilter too long (max 446 bytes, 32 prefixes)";
+        return bail(CTMR_E_INVALID);
+    }
+#define CUC(call)                                                              \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) {                                               \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);       \
+            return bail(e_ == cudaErrorMemoryAllocation ? CTMR_E_NOMEM : CTMR_E_CUDA); \
+        }                                                                      \
+    } while (0)
+    CUC(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10) {
+        c->err = "libctmr is built for sm_100a (B200) only";
+        return bail(CTMR_E_NO_DEVICE);
+    }
+    c->sm_count = prop.multiProcessorCount;
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const uint64_t cap = pow2_at_least(cfg->table_capacity ? cfg->table_capacity : (1ull << 20));
+    if (cap > (1ull << 32) - 16) {
+        c->err = "table_capacity above 2^32 slots";
+        return bail(CTMR_E_INVALID);
+    }
+    c->st.table_mask = cap - 1;
+    CUC(cudaMalloc(&c->st.table, cap * sizeof(KnownSlot)));
+    CUC(cudaMemsetAsync(c->st.table, 0, cap * sizeof(KnownSlot), c->stream));
+    const uint32_t plog = cfg->pair_capacity_log2 ? cfg->pair_capacity_log2 : 24;
+    c->st.pair_mask = (1ull << plog) - 1;
+    CUC(cudaMalloc(&c->st.pairs, (c->st.pair_mask + 1) * sizeof(PairSlot)));
+    CUC(cudaMemsetAsync(c->st.pairs, 0, (c->st.pair_mask + 1) * sizeof(PairSlot), c->stream));
+    c->st.max_issuers = cfg->max_issuers ? cfg->max_issuers : 65536;
+    CUC(cudaMalloc(&c->st.issuer_counts, c->st.max_issuers * sizeof(unsigned long long)));
+    CUC(cudaMemsetAsync(c->st.issuer_counts, 0, c->st.max_issuers * sizeof(unsigned long long), c->stream));
+    CUC(cudaMalloc(&c->small_dev, 128 * sizeof(unsigned long long)));
+    CUC(cudaMemsetAsync(c->small_dev, 0, 128 * sizeof(unsigned long long), c->stream));
+    c->st.status_counts = c->small_dev + 64;  // [8]
+    c->st.slots_used = c->small_dev + 72;     // [1]
+    c->st.error_flag = reinterpret_cast<int*>(c->small_dev + 73);
+    c->stage_entries = cfg->max_batch_entries ? (cfg->max_batch_entries < kStageEntries ? cfg->max_batch_entries : kStageEntries)
+                                              : kStageEntries;
+    const uint64_t want_bytes = cfg->max_batch_bytes ? cfg->max_batch_bytes : c->stage_entries * 2048ull;
+    c->stage_bytes = want_bytes < kStageBytes ? want_bytes : kStageBytes;
+    CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+    *out = c;
+    return CTMR_OK;
+}
+
+void ctmr_destroy(ctmr_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (Stage& s : c->stages) {
+        cudaFree(s.blob); cudaFree(s.offsets); cudaFree(s.issuer_idx); cudaFree(s.status); cudaFree(s.sha);
+        cudaFree(s.exp_hour); cudaFree(s.serial_off); cudaFree(s.serial_len); cudaFree(s.was_unknown); cudaFree(s.first);
+        cudaFree(s.keys); cudaFree(s.slot_of); cudaFree(s.pair_slot);
+        if (s.reduced) cudaEventDestroy(s.reduced);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(c->st.table); cudaFree(c->st.pairs); cudaFree(c->st.issuer_counts); cudaFree(c->small_dev);
+    cudaFree(c->issuer_map_dev); cudaFree(c->keys_scratch); cudaFree(c->slot_scratch); cudaFree(c->pair_scratch);
+    cudaFree(c->bits_scratch);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------------------ issuers
+int ctmr_register_issuers(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t* dense_out) {
+    if (!c || (n && (!blob || !offsets || !dense_out))) return fail(c, CTMR_E_INVALID, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    std::vector<uint32_t> fresh;  // positions whose DER has not been seen before
+    std::vector<std::string> ders(n);
+    for (uint32_t k = 0; k < n; ++k) {
+        if (offsets[k + 1] < offsets[k]) return fail(c, CTMR_E_INVALID, "issuer offsets not monotonic");
+        ders[k].assign(reinterpret_cast<const char*>(blob + offsets[k]), (size_t)(offsets[k + 1] - offsets[k]));
+        auto it = c->issuer_by_der.find(ders[k]);
+        if (it != c->issuer_by_der.end()) {
+            dense_out[k] = it->second;
+        } else {
+            bool dup = false;
+            for (uint32_t f : fresh)
+                if (ders[f] == ders[k]) { dup = true; break; }
+            if (!dup) fresh.push_back(k);
+            dense_out[k] = CTMR_ISSUER_NONE;  // patched below
+        }
+    }
+    if (!fresh.empty()) {
+        // only never-seen certificates go to the GPU: parse + SHA-256(SPKI) there, ids come back
+        std::vector<uint8_t> packed;
+        std::vector<uint64_t> poff(1, 0);
+        for (uint32_t f : fresh) {
+            packed.insert(packed.end(), ders[f].begin(), ders[f].end());
+            poff.push_back(packed.size());
+        }
+        const uint32_t nf = (uint32_t)fresh.size();
+        uint8_t *d_blob = nullptr, *d_dig = nullptr, *d_ok = nullptr;
+        uint64_t* d_off = nullptr;
+        CU(c, cudaMalloc(&d_blob, packed.size() + 64));
+        CU(c, cudaMalloc(&d_off, poff.size() * sizeof(uint64_t)));
+        CU(c, cudaMalloc(&d_dig, nf * 32));
+        CU(c, cudaMalloc(&d_ok, nf));
+        CU(c, cudaMemcpyAsync(d_blob, packed.data(), packed.size(), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(d_off, poff.data(), poff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        CU(c, launch_issuer_prepare(d_blob, d_off, nf, d_dig, d_ok, c->stream));
+        std::vector<uint8_t> dig(nf * 32), ok(nf);
+        CU(c, cudaMemcpyAsync(dig.data(), d_dig, nf * 32, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(ok.data(), d_ok, nf, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(d_blob); cudaFree(d_off); cudaFree(d_dig); cudaFree(d_ok);
+        for (uint32_t i = 0; i < nf; ++i) {
+            uint32_t idx = CTMR_ISSUER_BAD;
+            if (ok[i]) {
+                std::string dk(reinterpret_cast<const char*>(dig.data() + 32 * i), 32);
+                auto it = c->issuer_by_digest.find(dk);
+                if (it != c->issuer_by_digest.end()) {
+                    idx = it->second;
+                } else {
+                    if (c->digests.size() >= c->st.max_issuers)
+                        return fail(c, CTMR_E_TOO_MANY_ISSUERS, "more distinct issuers than config.max_issuers");
+                    idx = (uint32_t)c->digests.size();
+                    std::array<uint8_t, 32> a;
+                    std::memcpy(a.data(), dig.data() + 32 * i, 32);
+                    c->digests.push_back(a);
+                    c->issuer_by_digest.emplace(std::move(dk), idx);
+                }
+            }
+            c->issuer_by_der.emplace(ders[fresh[i]], idx);
+        }
+        for (uint32_t k = 0; k < n; ++k)
+            if (dense_out[k] == CTMR_ISSUER_NONE) dense_out[k] = c->issuer_by_der[ders[k]];
+    }
+    return CTMR_OK;
+}
+
+int ctmr_issuer_digest(ctmr_ctx* c, uint32_t idx, uint8_t out[32]) {
+    if (!c || !out || idx >= c->digests.size()) return fail(c, CTMR_E_INVALID, "no such issuer");
+    std::memcpy(out, c->digests[idx].data(), 32);
+    return CTMR_OK;
+}
+
+uint32_t ctmr_issuer_count(ctmr_ctx* c) { return c ? (uint32_t)c->digests.size() : 0; }
+
+// ------------------------------------------------------------------------------------------------ device entry points
+int ctmr_map_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, void* stream) {
+    if (!c || !b || !o) return fail(c, CTMR_E_INVALID, "bad argument");
+    if (b->n && (!b->blob || !b->offsets)) return fail(c, CTMR_E_INVALID, "null batch buffers");
+    CU(c, cudaSetDevice(c->device));
+    MapParams p;
+    fill_map_params(c, b, o, p);
+    CU(c, launch_map(p, c->sm_count, stream ? (cudaStream_t)stream : c->stream));
+    return CTMR_OK;
+}
+
+int ctmr_reduce_device(ctmr_ctx* c, const ctmr_key* keys, uint64_t m, uint8_t* was_unknown, uint8_t* first, void* stream) {
+    if (!c || (m && !keys)) return fail(c, CTMR_E_INVALID, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_scratch(c, m);
+    if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    return reduce_on(c, keys, m, c->slot_scratch, c->pair_scratch, was_unknown ? was_unknown : c->bits_scratch,
+                     first ? first : c->bits_scratch + m, s);
+}
+
+int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, void* stream) {
+    if (!c || !b || !o) return fail(c, CTMR_E_INVALID, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_scratch(c, b->n);
+    if (rc) return rc;
+    ctmr_dev_out oo = *o;
+    if (!oo.keys) oo.keys = c->keys_scratch;
+    rc = ctmr_map_device(c, b, &oo, stream);
+    if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    return reduce_on(c, oo.keys, b->n, c->slot_scratch, c->pair_scratch, oo.was_unknown ? oo.was_unknown : c->bits_scratch,
+                     oo.first_issuer_hour ? oo.first_issuer_hour : c->bits_scratch + b->n, s);
+}
+
+int ctmr_partition_keys_device(ctmr_ctx* c, const ctmr_key* keys, uint64_t n, uint32_t world, ctmr_key* by_owner,
+                               uint32_t* src_pos, uint64_t* owner_counts, void* stream) {
+    if (!c || world == 0 || world > 64 || !owner_counts || (n && (!keys || !by_owner || !src_pos)))
+        return fail(c, CTMR_E_INVALID, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, launch_partition(keys, n, world, by_owner, src_pos, reinterpret_cast<unsigned long long*>(owner_counts),
+                           c->small_dev, stream ? (cudaStream_t)stream : c->stream));
+    return CTMR_OK;
+}
+
+int ctmr_scatter_bits_device(ctmr_ctx* c, const uint8_t* a, const uint8_t* b, const uint32_t* src_pos, uint64_t m,
+                             uint8_t* a_dst, uint8_t* b_dst, void* stream) {
+    if (!c || (m && (!a || !b || !src_pos))) return fail(c, CTMR_E_INVALID, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, launch_scatter_bits(a, b, src_pos, m, a_dst, b_dst, stream ? (cudaStream_t)stream : c->stream));
+    return CTMR_OK;
+}
+
+int ctmr_read_histogram_device(ctmr_ctx* c, uint64_t* counts_dst, uint32_t n_slots, uint64_t* status_dst, void* stream) {
+    if (!c || n_slots > c->st.max_issuers) return fail(c, CTMR_E_INVALID, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    if (counts_dst && n_slots)
+        CU(c, cudaMemcpyAsync(counts_dst, c->st.issuer_counts, n_slots * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    if (status_dst)
+        CU(c, cudaMemcpyAsync(status_dst, c->st.status_counts, CTMR_ST__COUNT * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    return CTMR_OK;
+}
+
+int ctmr_reset_device(ctmr_ctx* c, void* stream) {
+    if (!c) return CTMR_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    CU(c, cudaMemsetAsync(c->st.table, 0, (c->st.table_mask + 1) * sizeof(KnownSlot), s));
+    CU(c, cudaMemsetAsync(c->st.pairs, 0, (c->st.pair_mask + 1) * sizeof(PairSlot), s));
+    CU(c, cudaMemsetAsync(c->st.issuer_counts, 0, c->st.max_issuers * sizeof(unsigned long long), s));
+    CU(c, cudaMemsetAsync(c->small_dev + 64, 0, 16 * sizeof(unsigned long long), s));
+    return CTMR_OK;
+}
+
+int ctmr_check_device(ctmr_ctx* c, void* stream) {
+    if (!c) return CTMR_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    int flag = 0;
+    CU(c, cudaMemcpyAsync(&flag, c->st.error_flag, sizeof flag, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    if (flag == CTMR_E_TABLE_FULL) return fail(c, CTMR_E_TABLE_FULL, "known-certificate table is full; raise config.table_capacity");
+    if (flag) return fail(c, CTMR_E_CUDA, "device-side failure flag set");
+    return CTMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ the host-buffer batch
+int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint64_t n, const uint8_t* issuer_blob,
+                       const uint64_t* issuer_offsets, uint32_t n_issuers, const uint32_t* issuer_idx, int64_t now_unix_ns,
+                       ctmr_out* out) {
+    if (!c || !out || (n && (!blob || !offsets))) return fail(c, CTMR_E_INVALID, "bad argument");
+    if (n == 0) return CTMR_OK;
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_stages(c);
+    if (rc) return rc;
+    // issuers of this batch -> dense indices (GPU work only for certificates never seen before)
+    const uint32_t* map_dev = nullptr;
+    if (n_issuers) {
+        std::vector<uint32_t> dense(n_issuers);
+        rc = ctmr_register_issuers(c, issuer_blob, issuer_offsets, n_issuers, dense.data());
+        if (rc) return rc;
+        if (n_issuers > c->issuer_map_cap) {
+            cudaFree(c->issuer_map_dev);
+            c->issuer_map_dev = nullptr;
+            c->issuer_map_cap = 0;
+            CU(c, cudaMalloc(&c->issuer_map_dev, (size_t)n_issuers * sizeof(uint32_t)));
+            c->issuer_map_cap = n_issuers;
+        }
+        CU(c, cudaMemcpyAsync(c->issuer_map_dev, dense.data(), n_issuers * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        map_dev = c->issuer_map_dev;
+    }
+    // pipeline: stage k = sub-batch k mod 3; H2D, map, insert, resolve, D2H each on the stage's stream.
+    // Sub-batch s+1 may only start inserting once s has resolved (lowest-index-wins needs every
+    // earlier entry in the table), expressed with one event per stage.
+    uint64_t lo = 0;
+    int sub = 0;
+    cudaEvent_t prev = nullptr;
+    while (lo < n) {
+        uint64_t hi = lo + c->stage_entries < n ? lo + c->stage_entries : n;
+        if (offsets[hi] - offsets[lo] > c->stage_bytes) {  // shrink to the byte budget
+            uint64_t a = lo, b = hi;                        // largest hi with bytes <= budget
+            while (a + 1 < b) {
+                uint64_t mid = (a + b) / 2;
+                if (offsets[mid] - offsets[lo] <= c->stage_bytes) a = mid; else b = mid;
+            }
+            hi = a;
+            if (hi == lo) return fail(c, CTMR_E_BATCH_TOO_LARGE, "a single entry exceeds the staging budget (config.max_batch_bytes)");
+        }
+        Stage& s = c->stages[sub % kStages];
+        const uint64_t cnt = hi - lo, bytes = offsets[hi] - offsets[lo];
+        CU(c, cudaMemcpyAsync(s.blob, blob + offsets[lo], bytes, cudaMemcpyHostToDevice, s.stream));
+        CU(c, cudaMemcpyAsync(s.offsets, offsets + lo, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        if (issuer_idx) CU(c, cudaMemcpyAsync(s.issuer_idx, issuer_idx + lo, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+        ctmr_dev_batch db{};
+        db.blob = s.blob - offsets[lo];  // offsets stay absolute
+        db.blob_bytes = offsets[hi];
+        db.offsets = s.offsets;
+        db.n = cnt;
+        db.issuer_idx = issuer_idx ? s.issuer_idx : nullptr;
+        db.issuer_map = map_dev;
+        db.issuer_map_len = n_issuers;
+        db.first_index = c->next_index + lo;
+        db.now_unix_ns = now_unix_ns;
+        ctmr_dev_out dout{};
+        dout.status = s.status;
+        dout.sha256 = out->sha256 ? s.sha : nullptr;
+        dout.exp_hour = s.exp_hour;
+        dout.serial_off = s.serial_off;
+        dout.serial_len = s.serial_len;
+        dout.keys = s.keys;
+        MapParams p;
+        fill_map_params(c, &db, &dout, p);
+        CU(c, launch_map(p, c->sm_count, s.stream));
+        if (prev) CU(c, cudaStreamWaitEvent(s.stream, prev, 0));
+        CU(c, launch_insert(c->st, s.keys, cnt, s.slot_of, s.stream));
+        CU(c, launch_resolve(c->st, s.keys, cnt, s.slot_of, s.pair_slot, s.was_unknown, s.stream));
+        CU(c, cudaEventRecord(s.reduced, s.stream));
+        prev = s.reduced;
+        CU(c, launch_resolve_pairs(c->st, s.keys, cnt, s.pair_slot, s.was_unknown, s.first, s.stream));
+        if (out->status) CU(c, cudaMemcpyAsync(out->status + lo, s.status, cnt, cudaMemcpyDeviceToHost, s.stream));
+        if (out->sha256) CU(c, cudaMemcpyAsync(out->sha256 + lo * 32, s.sha, cnt * 32, cudaMemcpyDeviceToHost, s.stream));
+        if (out->exp_hour) CU(c, cudaMemcpyAsync(out->exp_hour + lo, s.exp_hour, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+        if (out->serial_off) CU(c, cudaMemcpyAsync(out->serial_off + lo, s.serial_off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (out->serial_len) CU(c, cudaMemcpyAsync(out->serial_len + lo, s.serial_len, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (out->was_unknown) CU(c, cudaMemcpyAsync(out->was_unknown + lo, s.was_unknown, cnt, cudaMemcpyDeviceToHost, s.stream));
+        if (out->first_issuer_hour) CU(c, cudaMemcpyAsync(out->first_issuer_hour + lo, s.first, cnt, cudaMemcpyDeviceToHost, s.stream));
+        lo = hi;
+        ++sub;
+    }
+    for (int k = 0; k < kStages && k < sub; ++k) CU(c, cudaStreamSynchronize(c->stages[k].stream));
+    c->next_index += n;
+    // pairs of stage s read the pair table after resolve(s); a later stage's resolve only ever
+    // raises inv_first for lower indices, which cannot exist: indices grow with the stage number.
+    return ctmr_check_device(c, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------ read side
+int ctmr_issuer_counts(ctmr_ctx* c, uint8_t* digests, uint64_t* counts, size_t* n) {
+    if (!c || !n) return fail(c, CTMR_E_INVALID, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    const size_t have = c->digests.size(), cap = *n;
+    const size_t take = have < cap ? have : cap;
+    if (take) {
+        if (counts) {
+            CU(c, cudaMemcpyAsync(counts, c->st.issuer_counts, take * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+        }
+        if (digests)
+            for (size_t i = 0; i < take; ++i) std::memcpy(digests + 32 * i, c->digests[i].data(), 32);
+    }
+    *n = take;
+    return CTMR_OK;
+}
+
+int ctmr_set_cardinality(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], uint64_t* out) {
+    if (!c || !digest || !out) return fail(c, CTMR_E_INVALID, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    *out = 0;
+    auto it = c->issuer_by_digest.find(std::string(reinterpret_cast<const char*>(digest), 32));
+    if (it == c->issuer_by_digest.end() || exp_hour > INT32_MAX || exp_hour < INT32_MIN) return CTMR_OK;
+    CU(c, cudaMemsetAsync(c->small_dev + 32, 0, sizeof(unsigned long long), c->stream));
+    CU(c, launch_cardinality(c->st, (int32_t)exp_hour, it->second, c->small_dev + 32, c->stream));
+    unsigned long long v = 0;
+    CU(c, cudaMemcpyAsync(&v, c->small_dev + 32, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    *out = v;
+    return CTMR_OK;
+}
+
+int ctmr_status_counters(ctmr_ctx* c, uint64_t out[CTMR_ST__COUNT]) {
+    if (!c || !out) return fail(c, CTMR_E_INVALID, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(out, c->st.status_counts, CTMR_ST__COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CTMR_OK;
+}
+
+int ctmr_table_stats(ctmr_ctx* c, uint64_t* used, uint64_t* capacity) {
+    if (!c) return CTMR_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    unsigned long long u = 0;
+    CU(c, cudaMemcpyAsync(&u, c->st.slots_used, sizeof u, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (used) *used = u;
+    if (capacity) *capacity = c->st.table_mask + 1;
+    return CTMR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,573 @@
+// ctmr_kernels.cu -- hand-written sm_100a kernels of the CT-entry map/reduce hot path.
+//
+// K_map      lane-per-certificate map: DER walk + certIsFilteredOut + SHA-256(leaf DER).
+//            Each lane streams ITS certificate through a private double-buffered shared-memory
+//            slot with per-lane TMA bulk copies (cp.async.bulk -> SASS UBLKCP) completing on a
+//            per-warp mbarrier pair, so global loads never occupy registers or the LSU while the
+//            INT pipe runs the 64-round compression.  (cmd/ct-fetch/ct-fetch.go:44-70,198-213,
+//            storage/types.go:171-178,339-346; fingerprint = crypto/sha256.Sum256(cert.Raw).)
+// K_insert   open-addressing find-or-insert of (exp_hour, issuer, raw serial) key records into the
+//            persistent known-certificate table; lowest global entry index wins via atomicMax on
+//            the complemented index (storage/knowncertificates.go:38-55 over SetInsert).
+// K_resolve  was_unknown = "I am the lowest index of my key"; per-issuer unique counts
+//            (Count()-sum semantics, cmd/storage-statistics/storage-statistics.go:44-53) with
+//            warp-aggregated atomics; (issuer, exp_hour) first-seen table insert.
+// K_pairs    first_issuer_hour bit (IssuerMetadata.Accumulate's seenExpDateBefore,
+//            storage/issuermetadata.go:95-108).
+// plus issuer preparation (SPKI SHA-256 = Issuer.ID digest, storage/types.go:124-130,155-159),
+// set-cardinality scan, and the multi-GPU key partition / bit scatter helpers.
+#include "ctmr_kernels.cuh"
+
+#include "ctmr_device.cuh"
+
+namespace ctmr {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + bulk async copy (TMA, non-tensor form)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared::cta bulk copy; src and dst 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+
+// ------------------------------------------------------------------------------------------------
+// K_map
+// ------------------------------------------------------------------------------------------------
+template <int WARPS, int CHUNK>
+struct MapCfg {
+    static constexpr int kSlot = CHUNK + 16;                 // +16: a record may start anywhere in a 16-byte line
+    static constexpr int kWarpBytes = 2 * 32 * kSlot;        // two stages x 32 lanes
+    static constexpr int kBlocksPerChunk = CHUNK / 64;
+    static constexpr size_t kSmem = (size_t)WARPS * kWarpBytes + (size_t)WARPS * 2 * sizeof(uint64_t);
+};
+
+template <int WARPS, int CHUNK>
+__global__ void __launch_bounds__(WARPS * 32) map_kernel(const __grid_constant__ MapParams p) {
+    using Cfg = MapCfg<WARPS, CHUNK>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* my_slots = smem + (size_t)warp * Cfg::kWarpBytes + (size_t)lane * Cfg::kSlot;  // stage s at + s*32*kSlot
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * Cfg::kWarpBytes) + warp * 2;
+    const uint32_t bar0 = smem_u32(&bars[0]), bar1 = smem_u32(&bars[1]);
+    const uint32_t slot0 = smem_u32(my_slots), slot1 = slot0 + 32 * Cfg::kSlot;
+    if (lane == 0) {
+        mbar_init(bar0, 32);
+        mbar_init(bar1, 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t parity = 0;  // bit s: phase parity the next wait on stage s expects
+
+    const uint64_t ngroups = (p.n + 31) >> 5;
+    const bool want_sha = p.sha256 != nullptr;
+    for (uint64_t g = (uint64_t)blockIdx.x * WARPS + warp; g < ngroups; g += (uint64_t)gridDim.x * WARPS) {
+        const uint64_t e = g * 32 + lane;
+        const bool act = e < p.n;
+        uint64_t off = 0, end = 0;
+        if (act) {
+            off = p.offsets[e];
+            end = p.offsets[e + 1];
+        }
+        // memory safety against malformed offset tables: an unusable record hashes as empty
+        bool bad_span = !act || end < off || end > p.blob_bytes || end - off > 0x7fffffffull;
+        const uint32_t L = bad_span ? 0u : (uint32_t)(end - off);
+        const uint8_t* d = p.blob + off;
+
+        // ---- streaming plan for the fingerprint
+        const uint64_t addr = reinterpret_cast<uint64_t>(d);
+        const uint32_t m = (uint32_t)(addr & 15u);
+        const uint8_t* src_base = reinterpret_cast<const uint8_t*>(addr & ~15ull);
+        const uint32_t nfull = L >> 6;
+        const uint32_t nb = want_sha && act ? nfull + 1u + ((L & 63u) >= 56u ? 1u : 0u) : 0u;  // padded blocks
+        const uint32_t ndata = want_sha && act ? (L + CHUNK - 1) / CHUNK : 0u;                  // chunks with data
+        const uint32_t nch = (nb + Cfg::kBlocksPerChunk - 1) / Cfg::kBlocksPerChunk;
+        uint32_t iters = warp_max_u32(nch);
+        iters = iters < 2u ? 2u : iters;
+
+        auto issue = [&](uint32_t c) {
+            const uint32_t bar = (c & 1u) ? bar1 : bar0;
+            if (c < ndata) {
+                const uint32_t db = min((uint32_t)CHUNK, L - c * CHUNK);
+                const uint32_t bytes = (m + db + 15u) & ~15u;
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_g2s((c & 1u) ? slot1 : slot0, src_base + (size_t)c * CHUNK, bytes, bar);
+            } else {
+                mbar_arrive(bar);
+            }
+        };
+        if (want_sha) {  // both stages in flight while this lane walks the TLV tree
+            issue(0);
+            issue(1);
+        }
+
+        // ---- map: x509 field extraction + certIsFilteredOut
+        ParsedCert pc;
+        uint32_t status = CTMR_ST_PARSE_ERR;
+        uint32_t issuer = CTMR_ISSUER_NONE;
+        int64_t exp_hour = 0;
+        if (act) {
+            const bool ok = !bad_span && parse_cert(d, L, pc);
+            if (ok) {
+                status = CTMR_ST_OK;
+                exp_hour = pc.not_after >= 0 ? pc.not_after / 3600 : -((-pc.not_after + 3599) / 3600);
+                if ((pc.flags & (PC_BC_VALID | PC_IS_CA)) == (PC_BC_VALID | PC_IS_CA)) {
+                    status = CTMR_ST_FILTER_CA;
+                } else if (!p.filter.log_expired &&
+                           (pc.not_after < p.now_sec || (pc.not_after == p.now_sec && p.now_frac_nonzero))) {
+                    status = CTMR_ST_FILTER_EXPIRED;
+                } else if (p.filter.filter_nonempty) {
+                    bool skip = true;
+                    const uint32_t cnl = (pc.flags & PC_HAS_CN) ? pc.cn_len : 0u;
+                    for (uint32_t q = 0; q < p.filter.n_prefix && skip; ++q) {
+                        const uint32_t po = p.filter.off[q], pl = p.filter.off[q + 1] - po;
+                        if (pl > cnl) continue;
+                        bool eq = true;
+                        for (uint32_t i = 0; i < pl; ++i) {
+                            if (__ldg(d + pc.cn_off + i) != p.filter.bytes[po + i]) {
+                                eq = false;
+                                break;
+                            }
+                        }
+                        if (eq) skip = false;
+                    }
+                    if (skip) status = CTMR_ST_FILTER_CN;
+                }
+                if (status == CTMR_ST_OK) {
+                    uint32_t k = p.issuer_idx ? p.issuer_idx[e] : CTMR_ISSUER_NONE;
+                    if (k != CTMR_ISSUER_NONE && p.issuer_map) k = k < p.issuer_map_len ? p.issuer_map[k] : CTMR_ISSUER_NONE;
+                    issuer = k;
+                    if (k == CTMR_ISSUER_NONE) status = CTMR_ST_NO_ISSUER;
+                    else if (k == CTMR_ISSUER_BAD) status = CTMR_ST_ISSUER_PARSE_ERR;
+                    else if (pc.serial_len > CTMR_MAX_SERIAL) status = CTMR_ST_SERIAL_TOO_LONG;
+                }
+            } else {
+                pc.serial_off = pc.serial_len = 0;
+            }
+            if (p.status) p.status[e] = (uint8_t)status;
+            if (p.exp_hour) p.exp_hour[e] = exp_hour;
+            if (p.serial_off) p.serial_off[e] = pc.serial_off;
+            if (p.serial_len) p.serial_len[e] = pc.serial_len;
+            if (p.keys) {
+                // 64-byte key record, written as four 16-byte stores
+                uint32_t kw[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) kw[i] = 0;
+                const bool valid = status == CTMR_ST_OK;
+                if (valid) {
+                    kw[0] = pc.serial_len;
+#pragma unroll
+                    for (int i = 0; i < (int)CTMR_MAX_SERIAL; ++i) {
+                        if ((uint32_t)i < pc.serial_len)
+                            kw[(i + 1) >> 2] |= (uint32_t)__ldg(d + pc.serial_off + i) << (8 * ((i + 1) & 3));
+                    }
+                }
+                const uint64_t gi = p.first_index + e;
+                uint4* kr = reinterpret_cast<uint4*>(p.keys + e);
+                kr[0] = make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)(int32_t)exp_hour, valid ? issuer : 0u);
+                kr[1] = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+                kr[2] = make_uint4(kw[4], kw[5], kw[6], kw[7]);
+                kr[3] = make_uint4(kw[8], kw[9], valid ? 1u : 0u, 0u);
+            }
+        }
+        if (p.status_counts) {  // certIsFilteredOut.* / insertCTWorker.Inserted counters, one atomic per value per warp
+            const uint32_t amask = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const uint32_t peers = __match_any_sync(amask, status);
+                if ((uint32_t)lane == (uint32_t)__ffs(peers) - 1u)
+                    atomicAdd(p.status_counts + status, (unsigned long long)__popc(peers));
+            }
+        }
+
+        // ---- fingerprint: SHA-256 over the record, streamed chunk by chunk through shared memory
+        if (want_sha) {
+            Sha256State st;
+            st.init();
+            const uint32_t sel = 0x0123u + 0x1111u * (m & 3u);  // PRMT: big-endian word starting at byte (m & 3)
+            for (uint32_t c = 0; c < iters; ++c) {
+                const uint32_t s = c & 1u;
+                mbar_wait(s ? bar1 : bar0, (parity >> s) & 1u);
+                parity ^= 1u << s;
+                if (c < nch) {
+                    const uint8_t* slot = my_slots + (size_t)s * 32 * Cfg::kSlot;
+#pragma unroll 1
+                    for (uint32_t bb = 0; bb < (uint32_t)Cfg::kBlocksPerChunk; ++bb) {
+                        const uint32_t b = c * Cfg::kBlocksPerChunk + bb;
+                        if (b >= nb) break;
+                        const uint32_t* sw = reinterpret_cast<const uint32_t*>(slot) + ((m + 64u * bb) >> 2);
+                        uint32_t x[17], w[16];
+#pragma unroll
+                        for (int i = 0; i < 17; ++i) x[i] = sw[i];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) w[i] = __byte_perm(x[i], x[i + 1], sel);
+                        if (b >= nfull) {  // trailing block(s): 0x80, zeros, 64-bit bit length
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) w[i] = sha256_pad_word(w[i], b * 64u + 4u * i, L);
+                            if (b == nb - 1u) {
+                                w[14] = L >> 29;
+                                w[15] = L << 3;
+                            }
+                        }
+                        sha256_compress(st, w);
+                    }
+                }
+                if (c + 2u < iters) issue(c + 2u);
+            }
+            if (act) {
+                uint4* o = reinterpret_cast<uint4*>(p.sha256 + e * 32);
+                o[0] = make_uint4(__byte_perm(st.h[0], 0, 0x0123), __byte_perm(st.h[1], 0, 0x0123),
+                                  __byte_perm(st.h[2], 0, 0x0123), __byte_perm(st.h[3], 0, 0x0123));
+                o[1] = make_uint4(__byte_perm(st.h[4], 0, 0x0123), __byte_perm(st.h[5], 0, 0x0123),
+                                  __byte_perm(st.h[6], 0, 0x0123), __byte_perm(st.h[7], 0, 0x0123));
+            }
+        }
+    }
+}
+
+template <int WARPS, int CHUNK>
+static cudaError_t launch_map_t(const MapParams& p, int sm_count, int ctas_per_sm, cudaStream_t s) {
+    using Cfg = MapCfg<WARPS, CHUNK>;
+    auto kern = map_kernel<WARPS, CHUNK>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if (err != cudaSuccess) return err;
+    const uint64_t ngroups = (p.n + 31) / 32;
+    uint64_t ctas = (uint64_t)sm_count * ctas_per_sm;  // persistent: a multiple of the SM count
+    const uint64_t need = (ngroups + WARPS - 1) / WARPS;
+    if (need < ctas) ctas = need ? need : 1;
+    kern<<<(unsigned)ctas, WARPS * 32, Cfg::kSmem, s>>>(p);
+    return cudaGetLastError();
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {
+    if (p.n == 0) return cudaSuccess;
+    // shape of the persistent grid; the defaults are the measured best (DESIGN.md "K_map tuning")
+    static const int warps = env_int("CTMR_MAP_WARPS", 4);
+    static const int chunk = env_int("CTMR_MAP_CHUNK", 256);
+    static const int cps = env_int("CTMR_MAP_CTAS_PER_SM", 0);
+    if (chunk == 512) {
+        if (warps == 2) return launch_map_t<2, 512>(p, sm_count, cps ? cps : 3, s);
+        if (warps == 6) return launch_map_t<6, 512>(p, sm_count, cps ? cps : 1, s);
+        return launch_map_t<4, 512>(p, sm_count, cps ? cps : 1, s);
+    }
+    if (warps == 8) return launch_map_t<8, 256>(p, sm_count, cps ? cps : 1, s);
+    if (warps == 2) return launch_map_t<2, 256>(p, sm_count, cps ? cps : 6, s);
+    return launch_map_t<4, 256>(p, sm_count, cps ? cps : 3, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_insert / K_resolve / K_pairs
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+__device__ __forceinline__ uint64_t key_hash(const uint32_t (&b)[12]) {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) h = mix64(h ^ (((uint64_t)b[i + 1] << 32) | b[i])) + 0x632BE59BD9B4E019ull * (i + 1);
+    return h;
+}
+
+__global__ void __launch_bounds__(256) insert_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
+                                                     uint32_t* __restrict__ slot_of) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint4* kr = reinterpret_cast<const uint4*>(keys + j);
+    const uint4 q0 = kr[0], q1 = kr[1], q2 = kr[2], q3 = kr[3];
+    if (q3.z == 0u) {  // not a Store-reaching entry
+        slot_of[j] = 0xFFFFFFFFu;
+        return;
+    }
+    const unsigned long long inv_idx = ~(((unsigned long long)q0.y << 32) | q0.x);
+    const uint32_t body[12] = {q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y};
+    const uint64_t h = key_hash(body);
+    const unsigned long long tag_ready = (h & ~3ull) | 2ull, tag_pending = (h & ~3ull) | 1ull;
+    uint64_t pos = (h >> 7) & st.table_mask;
+    uint32_t probes = 0;
+    for (;;) {
+        KnownSlot* sl = st.table + pos;
+        unsigned long long t = ld_volatile_u64(&sl->tag);
+        if (t == 0ull) {
+            t = atomicCAS(&sl->tag, 0ull, tag_pending);
+            if (t == 0ull) {  // claimed: publish the key bytes, then flip to ready
+                uint4* bp = reinterpret_cast<uint4*>(sl->body);
+                bp[0] = make_uint4(body[0], body[1], body[2], body[3]);
+                bp[1] = make_uint4(body[4], body[5], body[6], body[7]);
+                bp[2] = make_uint4(body[8], body[9], body[10], body[11]);
+                __threadfence();
+                atomicExch(&sl->tag, tag_ready);
+                atomicMax(&sl->inv_first, inv_idx);
+                atomicAdd(st.slots_used, 1ull);
+                break;
+            }
+        }
+        if ((t & ~3ull) == (h & ~3ull)) {
+            if ((t & 3ull) == 1ull) continue;  // another thread is publishing this slot: look again
+            __threadfence();
+            const uint4* bp = reinterpret_cast<const uint4*>(sl->body);
+            const uint4 b0 = bp[0], b1 = bp[1], b2 = bp[2];
+            const bool same = b0.x == body[0] && b0.y == body[1] && b0.z == body[2] && b0.w == body[3] && b1.x == body[4] &&
+                              b1.y == body[5] && b1.z == body[6] && b1.w == body[7] && b2.x == body[8] && b2.y == body[9] &&
+                              b2.z == body[10] && b2.w == body[11];
+            if (same) {
+                atomicMax(&sl->inv_first, inv_idx);
+                break;
+            }
+        }
+        pos = (pos + 1) & st.table_mask;
+        if (++probes > 4096u) {  // table effectively full
+            atomicExch(st.error_flag, CTMR_E_TABLE_FULL);
+            pos = 0xFFFFFFFFull;
+            break;
+        }
+    }
+    slot_of[j] = (uint32_t)pos;
+}
+
+__global__ void __launch_bounds__(256) resolve_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
+                                                      const uint32_t* __restrict__ slot_of, uint32_t* __restrict__ pair_slot,
+                                                      uint8_t* __restrict__ was_unknown) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = j < m;
+    bool unknown = false;
+    uint32_t issuer = 0;
+    int32_t hour = 0;
+    unsigned long long inv_idx = 0;
+    if (in) {
+        const uint32_t s = slot_of[j];
+        if (s != 0xFFFFFFFFu) {
+            const uint4 q0 = reinterpret_cast<const uint4*>(keys + j)[0];
+            inv_idx = ~(((unsigned long long)q0.y << 32) | q0.x);
+            hour = (int32_t)q0.z;
+            issuer = q0.w;
+            unknown = st.table[s].inv_first == inv_idx;  // I am the first sighting of this key
+        }
+        was_unknown[j] = unknown ? 1 : 0;
+    }
+    // per-issuer unique count: one atomic per distinct issuer per warp
+    const uint32_t umask = __ballot_sync(0xffffffffu, unknown);
+    uint32_t ps = 0xFFFFFFFFu;
+    if (unknown) {
+        const uint32_t peers = __match_any_sync(umask, issuer);
+        if ((threadIdx.x & 31u) == (uint32_t)__ffs(peers) - 1u && issuer < st.max_issuers)
+            atomicAdd(st.issuer_counts + issuer, (unsigned long long)__popc(peers));
+        // (issuer, exp_hour) first-seen table: 64-bit key claims and identifies in one CAS
+        const unsigned long long pk = ((((unsigned long long)issuer) << 32) | (uint32_t)hour) + 1ull;
+        uint64_t pos = mix64(pk) & st.pair_mask;
+        for (uint32_t probes = 0;; ++probes) {
+            unsigned long long cur = ld_volatile_u64(&st.pairs[pos].key);
+            if (cur == 0ull) cur = atomicCAS(&st.pairs[pos].key, 0ull, pk);
+            if (cur == 0ull || cur == pk) {
+                atomicMax(&st.pairs[pos].inv_first, inv_idx);
+                ps = (uint32_t)pos;
+                break;
+            }
+            pos = (pos + 1) & st.pair_mask;
+            if (probes > 4096u) {
+                atomicExch(st.error_flag, CTMR_E_TABLE_FULL);
+                break;
+            }
+        }
+    }
+    if (in) pair_slot[j] = ps;
+}
+
+__global__ void __launch_bounds__(256) pairs_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
+                                                    const uint32_t* __restrict__ pair_slot,
+                                                    const uint8_t* __restrict__ was_unknown,
+                                                    uint8_t* __restrict__ first_issuer_hour) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    uint8_t first = 0;
+    const uint32_t ps = pair_slot[j];
+    if (was_unknown[j] && ps != 0xFFFFFFFFu) {
+        const uint4 q0 = reinterpret_cast<const uint4*>(keys + j)[0];
+        const unsigned long long inv_idx = ~(((unsigned long long)q0.y << 32) | q0.x);
+        first = st.pairs[ps].inv_first == inv_idx ? 1 : 0;
+    }
+    first_issuer_hour[j] = first;
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+cudaError_t launch_insert(const DeviceState& st, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, cudaStream_t s) {
+    if (!m) return cudaSuccess;
+    insert_kernel<<<blocks_for(m, 256), 256, 0, s>>>(st, keys, m, slot_of);
+    return cudaGetLastError();
+}
+cudaError_t launch_resolve(const DeviceState& st, const ctmr_key* keys, uint64_t m, const uint32_t* slot_of,
+                           uint32_t* pair_slot, uint8_t* was_unknown, cudaStream_t s) {
+    if (!m) return cudaSuccess;
+    resolve_kernel<<<blocks_for(m, 256), 256, 0, s>>>(st, keys, m, slot_of, pair_slot, was_unknown);
+    return cudaGetLastError();
+}
+cudaError_t launch_resolve_pairs(const DeviceState& st, const ctmr_key* keys, uint64_t m, const uint32_t* pair_slot,
+                                 const uint8_t* was_unknown, uint8_t* first_issuer_hour, cudaStream_t s) {
+    if (!m) return cudaSuccess;
+    pairs_kernel<<<blocks_for(m, 256), 256, 0, s>>>(st, keys, m, pair_slot, was_unknown, first_issuer_hour);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// issuers: x509.ParseCertificate(Chain[0]) + SHA-256(RawSubjectPublicKeyInfo)
+// ------------------------------------------------------------------------------------------------
+__global__ void issuer_prepare_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ offsets, uint32_t n,
+                                      uint8_t* __restrict__ digests, uint8_t* __restrict__ ok) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint64_t off = offsets[k], end = offsets[k + 1];
+    ParsedCert pc;
+    bool good = end >= off && end - off <= 0x7fffffffull && parse_cert(blob + off, (uint32_t)(end - off), pc);
+    uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (good) sha256_global(blob + off + pc.spki_off, pc.spki_len, h);
+    for (int i = 0; i < 8; ++i) {
+        digests[k * 32 + 4 * i + 0] = (uint8_t)(h[i] >> 24);
+        digests[k * 32 + 4 * i + 1] = (uint8_t)(h[i] >> 16);
+        digests[k * 32 + 4 * i + 2] = (uint8_t)(h[i] >> 8);
+        digests[k * 32 + 4 * i + 3] = (uint8_t)h[i];
+    }
+    ok[k] = good ? 1 : 0;
+}
+
+cudaError_t launch_issuer_prepare(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint8_t* digests, uint8_t* ok,
+                                  cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    issuer_prepare_kernel<<<blocks_for(n, 64), 64, 0, s>>>(blob, offsets, n, digests, ok);
+    return cudaGetLastError();
+}
+
+// SetCardinality("serials::<expDate>::<issuer>"): count ready slots of that set
+__global__ void __launch_bounds__(256) cardinality_kernel(DeviceState st, int32_t hour, uint32_t issuer,
+                                                          unsigned long long* out) {
+    unsigned long long local = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= st.table_mask; i += (uint64_t)gridDim.x * blockDim.x) {
+        const KnownSlot* sl = st.table + i;
+        if ((sl->tag & 3ull) == 2ull && sl->body[0] == (uint32_t)hour && sl->body[1] == issuer) ++local;
+    }
+    local = __reduce_add_sync(0xffffffffu, (unsigned)local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+cudaError_t launch_cardinality(const DeviceState& st, int32_t hour, uint32_t issuer, unsigned long long* out,
+                               cudaStream_t s) {
+    cardinality_kernel<<<148 * 8, 256, 0, s>>>(st, hour, issuer, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU routing helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) owner_count_kernel(const ctmr_key* __restrict__ keys, uint64_t n, uint32_t world,
+                                                          unsigned long long* __restrict__ counts) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    uint32_t owner = 0;
+    if (j < n) {
+        const uint4 q0 = reinterpret_cast<const uint4*>(keys + j)[0];
+        valid = reinterpret_cast<const uint4*>(keys + j)[3].z != 0u;
+        owner = key_owner((int32_t)q0.z, q0.w, world);
+    }
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+        const uint32_t peers = __match_any_sync(vmask, owner);
+        if ((threadIdx.x & 31u) == (uint32_t)__ffs(peers) - 1u) atomicAdd(counts + owner, (unsigned long long)__popc(peers));
+    }
+}
+
+__global__ void owner_scan_kernel(const unsigned long long* counts, uint32_t world, unsigned long long* cursors) {
+    unsigned long long acc = 0;
+    for (uint32_t w = 0; w < world; ++w) {
+        cursors[w] = acc;
+        acc += counts[w];
+    }
+}
+
+__global__ void __launch_bounds__(256) owner_scatter_kernel(const ctmr_key* __restrict__ keys, uint64_t n, uint32_t world,
+                                                            unsigned long long* __restrict__ cursors,
+                                                            ctmr_key* __restrict__ out, uint32_t* __restrict__ src_pos) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    uint32_t owner = 0;
+    uint4 q0, q1, q2, q3;
+    if (j < n) {
+        const uint4* kr = reinterpret_cast<const uint4*>(keys + j);
+        q0 = kr[0]; q1 = kr[1]; q2 = kr[2]; q3 = kr[3];
+        valid = q3.z != 0u;
+        owner = key_owner((int32_t)q0.z, q0.w, world);
+    }
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+        const uint32_t peers = __match_any_sync(vmask, owner);
+        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+        unsigned long long base = 0;
+        if ((threadIdx.x & 31u) == leader) base = atomicAdd(cursors + owner, (unsigned long long)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const uint64_t dst = base + __popc(peers & ((1u << (threadIdx.x & 31u)) - 1u));
+        uint4* o = reinterpret_cast<uint4*>(out + dst);
+        o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3;
+        src_pos[dst] = (uint32_t)j;
+    }
+}
+
+cudaError_t launch_partition(const ctmr_key* keys, uint64_t n, uint32_t world, ctmr_key* keys_by_owner, uint32_t* src_pos,
+                             unsigned long long* owner_counts, unsigned long long* cursors, cudaStream_t s) {
+    cudaError_t err = cudaMemsetAsync(owner_counts, 0, sizeof(unsigned long long) * world, s);
+    if (err != cudaSuccess || !n) return err;
+    owner_count_kernel<<<blocks_for(n, 256), 256, 0, s>>>(keys, n, world, owner_counts);
+    owner_scan_kernel<<<1, 1, 0, s>>>(owner_counts, world, cursors);
+    owner_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(keys, n, world, cursors, keys_by_owner, src_pos);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) scatter_bits_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                           const uint32_t* __restrict__ src_pos, uint64_t m,
+                                                           uint8_t* __restrict__ a_dst, uint8_t* __restrict__ b_dst) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint32_t d = src_pos[j];
+    if (a_dst) a_dst[d] = a[j];
+    if (b_dst) b_dst[d] = b[j];
+}
+
+cudaError_t launch_scatter_bits(const uint8_t* a, const uint8_t* b, const uint32_t* src_pos, uint64_t m, uint8_t* a_dst,
+                                uint8_t* b_dst, cudaStream_t s) {
+    if (!m) return cudaSuccess;
+    scatter_bits_kernel<<<blocks_for(m, 256), 256, 0, s>>>(a, b, src_pos, m, a_dst, b_dst);
+    return cudaGetLastError();
+}
+
+}  // namespace ctmr

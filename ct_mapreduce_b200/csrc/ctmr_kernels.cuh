@@ -1,0 +1,85 @@
+// ctmr_kernels.cuh -- launch-side declarations shared by ctmr_kernels.cu and ctmr_api.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ctmr.h"
+
+namespace ctmr {
+
+// issuerCNFilter, pre-split on ',' by the host (strings.Split, ct-fetch.go:58): prefixes are raw bytes.
+struct FilterCfg {
+    uint32_t filter_nonempty;  // len(*ctconfig.IssuerCNFilter) != 0
+    uint32_t n_prefix;
+    uint32_t log_expired;
+    uint32_t flags;            // CTMR_F_*
+    uint16_t off[33];          // prefix p = bytes[off[p] .. off[p+1])
+    uint8_t bytes[446];
+};
+static_assert(sizeof(FilterCfg) == 16 + 66 + 446, "FilterCfg layout");
+
+// known-certificate slot: 64 bytes = two 32-byte sectors
+struct __align__(16) KnownSlot {
+    unsigned long long inv_first;  // ~(lowest global entry index seen for this key); 0 = none yet
+    unsigned long long tag;        // 0 empty | (hash & ~3)|1 pending | (hash & ~3)|2 ready
+    uint32_t body[12];             // exp_hour, issuer, {serial_len, serial[39]}
+};
+static_assert(sizeof(KnownSlot) == 64, "KnownSlot layout");
+
+struct __align__(16) PairSlot {
+    unsigned long long key;        // ((issuer << 32) | (uint32)exp_hour) + 1; 0 = empty
+    unsigned long long inv_first;  // ~(lowest index among was-unknown entries of this (issuer, hour))
+};
+
+struct DeviceState {
+    KnownSlot* table;
+    uint64_t table_mask;       // capacity - 1
+    PairSlot* pairs;
+    uint64_t pair_mask;
+    unsigned long long* issuer_counts;  // [max_issuers]
+    uint32_t max_issuers;
+    unsigned long long* status_counts;  // [CTMR_ST__COUNT]
+    unsigned long long* slots_used;     // [1]
+    int* error_flag;                    // [1]: 0 ok, CTMR_E_TABLE_FULL...
+};
+
+struct MapParams {
+    const uint8_t* blob;
+    uint64_t blob_bytes;
+    const uint64_t* offsets;
+    uint64_t n;
+    const uint32_t* issuer_idx;
+    const uint32_t* issuer_map;
+    uint32_t issuer_map_len;
+    uint32_t pad;
+    uint64_t first_index;
+    int64_t now_sec;
+    uint32_t now_frac_nonzero;
+    uint32_t pad2;
+    uint8_t* status;
+    uint8_t* sha256;
+    int64_t* exp_hour;
+    uint32_t* serial_off;
+    uint32_t* serial_len;
+    ctmr_key* keys;
+    unsigned long long* status_counts;
+    FilterCfg filter;
+};
+
+cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_insert(const DeviceState& st, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, cudaStream_t s);
+cudaError_t launch_resolve(const DeviceState& st, const ctmr_key* keys, uint64_t m, const uint32_t* slot_of,
+                           uint32_t* pair_slot, uint8_t* was_unknown, cudaStream_t s);
+cudaError_t launch_resolve_pairs(const DeviceState& st, const ctmr_key* keys, uint64_t m, const uint32_t* pair_slot,
+                                 const uint8_t* was_unknown, uint8_t* first_issuer_hour, cudaStream_t s);
+cudaError_t launch_issuer_prepare(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint8_t* digests,
+                                  uint8_t* ok, cudaStream_t s);
+cudaError_t launch_cardinality(const DeviceState& st, int32_t exp_hour, uint32_t issuer, unsigned long long* out,
+                               cudaStream_t s);
+cudaError_t launch_partition(const ctmr_key* keys, uint64_t n, uint32_t world, ctmr_key* keys_by_owner,
+                             uint32_t* src_pos, unsigned long long* owner_counts, unsigned long long* cursors,
+                             cudaStream_t s);
+cudaError_t launch_scatter_bits(const uint8_t* a, const uint8_t* b, const uint32_t* src_pos, uint64_t m, uint8_t* a_dst,
+                                uint8_t* b_dst, cudaStream_t s);
+
+}  // namespace ctmr

@@ -265,10 +265,10 @@ CTMR_HD uint8_t* ctmr_emit_issuer_name(uint8_t* p, const ctmr_synth_cfg* c, uint
 /* ---------------------------------------------------------------- keys and signatures */
 
 CTMR_HD void ctmr_synth_ec_point(uint32_t idx, uint8_t* out64) {
-    const uint8_t tbl[16][64] = {
+    const uint8_t tbl[64][64] = {
 #include "ctmr_synth_ecpoints.inc"
     };
-    for (uint32_t i = 0; i < 64; ++i) out64[i] = tbl[idx & 15u][i];
+    for (uint32_t i = 0; i < 64; ++i) out64[i] = tbl[idx & 63u][i];
 }
 
 /* SPKI: 294 octets (RSA-2048, e=65537) or 91 octets (P-256) */
@@ -277,7 +277,8 @@ CTMR_HD uint8_t* ctmr_emit_spki(uint8_t* p, const ctmr_synth_cfg* c, uint32_t do
         const uint8_t h[27] = {0x30, 0x59, 0x30, 0x13, 0x06, 0x07, 0x2a, 0x86, 0x48, 0xce, 0x3d, 0x02, 0x01, 0x06,
                                0x08, 0x2a, 0x86, 0x48, 0xce, 0x3d, 0x03, 0x01, 0x07, 0x03, 0x42, 0x00, 0x04};
         p = ctmr_emit(p, h, 27);
-        ctmr_synth_ec_point((uint32_t)ctmr_synth_rand(c, domain, id, 63), p);
+        /* issuers (domain 2) take distinct table rows so that every CA has its own Issuer.ID */
+        ctmr_synth_ec_point(domain == 2 ? (uint32_t)(id >> 3) : (uint32_t)ctmr_synth_rand(c, domain, id, 63), p);
         return p + 64;
     }
     const uint8_t h[33] = {0x30, 0x82, 0x01, 0x22, 0x30, 0x0d, 0x06, 0x09, 0x2a, 0x86, 0x48, 0x86, 0xf7, 0x0d, 0x01, 0x01, 0x01,

@@ -1,0 +1,232 @@
+"""Host-side mirror of the reference interface for the CT map/reduce path, over the C ABI.
+
+The reference is Go (no toolchain in this image), so this module plays the part the Go shim plays
+in production: it packs batches, calls libctmr through the very same C entry
+points, and exposes the results under the reference's names:
+
+    GpuCertDatabase.store_batch        <- insertCTWorker loop body + FilesystemDatabase.Store
+                                          (cmd/ct-fetch/ct-fetch.go:191-245, storage/filesystemdatabase.go:158-211)
+    GpuCertDatabase.get_known_certificates(exp_hour, issuer).count()
+                                       <- KnownCertificates.Count (storage/knowncertificates.go:57-63)
+    GpuCertDatabase.issuer_counts      <- the per-issuer sum of cmd/storage-statistics/storage-statistics.go:44-53
+    GpuCertDatabase.status_counters    <- metrics certIsFilteredOut.{CA,expired,cn-filtered}, insertCTWorker.Inserted
+
+All arithmetic happens in the CUDA kernels; nothing here parses, hashes or de-duplicates.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import CtmrError
+
+
+@dataclass
+class BatchResult:
+    """Per-entry outputs of one batch (numpy arrays in host memory)."""
+    status: np.ndarray
+    sha256: np.ndarray | None
+    exp_hour: np.ndarray
+    serial_off: np.ndarray
+    serial_len: np.ndarray
+    was_unknown: np.ndarray
+    first_issuer_hour: np.ndarray
+
+
+class KnownCertificatesView:
+    """Read side of storage.KnownCertificates for one (expDate, issuer) (knowncertificates.go:57-63)."""
+
+    def __init__(self, db: "GpuCertDatabase", exp_hour: int, issuer_digest: bytes):
+        self._db, self.exp_hour, self.issuer_digest = db, int(exp_hour), bytes(issuer_digest)
+
+    def count(self) -> int:
+        out = C.c_uint64(0)
+        d = (C.c_uint8 * 32).from_buffer_copy(self.issuer_digest)
+        self._db._check(self._db._lib.ctmr_set_cardinality(self._db._h, self.exp_hour, d, C.byref(out)))
+        return out.value
+
+
+class GpuCertDatabase:
+    """One ctmr_ctx = one GPU's share of the known-certificate state."""
+
+    def __init__(self, device: int = 0, table_capacity: int = 1 << 22, issuer_cn_filter: bytes | str = b"",
+                 log_expired_entries: bool = False, flags: int = 0, max_issuers: int = 0, max_batch_entries: int = 0,
+                 max_batch_bytes: int = 0, pair_capacity_log2: int = 0):
+        self._lib = capi.load()
+        if isinstance(issuer_cn_filter, str):
+            issuer_cn_filter = issuer_cn_filter.encode()
+        self._filter = bytes(issuer_cn_filter)
+        cfg = capi.Config()
+        cfg.struct_size = C.sizeof(capi.Config)
+        cfg.device = device
+        cfg.table_capacity = table_capacity
+        cfg.max_batch_entries = max_batch_entries
+        cfg.max_batch_bytes = max_batch_bytes
+        cfg.max_issuers = max_issuers
+        cfg.pair_capacity_log2 = pair_capacity_log2
+        cfg.issuer_cn_filter = self._filter
+        cfg.issuer_cn_filter_len = len(self._filter)
+        cfg.log_expired_entries = int(bool(log_expired_entries))
+        cfg.flags = flags
+        h = C.c_void_p()
+        rc = self._lib.ctmr_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise CtmrError(rc, (self._lib.ctmr_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self.flags = flags
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CtmrError(rc, (self._lib.ctmr_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ctmr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ------------------------------------------------------------------ issuers
+    def register_issuers(self, issuer_blob: np.ndarray, issuer_offsets: np.ndarray) -> np.ndarray:
+        """NewIssuer(x509.ParseCertificate(Chain[0])) for each certificate -> dense indices."""
+        issuer_blob = np.ascontiguousarray(issuer_blob, np.uint8)
+        issuer_offsets = np.ascontiguousarray(issuer_offsets, np.uint64)
+        n = issuer_offsets.size - 1
+        out = np.zeros(max(n, 1), np.uint32)
+        self._check(self._lib.ctmr_register_issuers(self._h, capi.ptr(issuer_blob), capi.ptr(issuer_offsets), n, capi.ptr(out)))
+        return out[:n]
+
+    def issuer_digest(self, dense_idx: int) -> bytes:
+        d = (C.c_uint8 * 32)()
+        self._check(self._lib.ctmr_issuer_digest(self._h, dense_idx, d))
+        return bytes(d)
+
+    # ------------------------------------------------------------------ the hot path, host buffers
+    def store_batch(self, blob, offsets, issuer_blob, issuer_offsets, issuer_idx, now_unix_ns: int,
+                    want_sha: bool = True, out: BatchResult | None = None) -> BatchResult:
+        """One batch through ctmr_process_batch (HOST buffers in, HOST buffers out)."""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = offsets.size - 1
+        n_iss = 0
+        if issuer_offsets is not None:
+            issuer_blob = np.ascontiguousarray(issuer_blob, np.uint8)
+            issuer_offsets = np.ascontiguousarray(issuer_offsets, np.uint64)
+            n_iss = issuer_offsets.size - 1
+        if issuer_idx is not None:
+            issuer_idx = np.ascontiguousarray(issuer_idx, np.uint32)
+        if out is None:
+            out = BatchResult(np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8) if want_sha else None, np.zeros(n, np.int64),
+                              np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.uint8))
+        o = capi.Out(capi.ptr(out.status), capi.ptr(out.sha256) if want_sha else None, capi.ptr(out.exp_hour),
+                     capi.ptr(out.serial_off), capi.ptr(out.serial_len), capi.ptr(out.was_unknown),
+                     capi.ptr(out.first_issuer_hour))
+        self._check(self._lib.ctmr_process_batch(self._h, capi.ptr(blob), capi.ptr(offsets), n,
+                                                 capi.ptr(issuer_blob) if n_iss else None,
+                                                 capi.ptr(issuer_offsets) if n_iss else None, n_iss,
+                                                 capi.ptr(issuer_idx), now_unix_ns, C.byref(o)))
+        return out
+
+    # ------------------------------------------------------------------ device-resident variants (torch tensors / raw pointers)
+    def map_device(self, batch: capi.DevBatch, out: capi.DevOut, stream=None):
+        self._check(self._lib.ctmr_map_device(self._h, C.byref(batch), C.byref(out), stream))
+
+    def reduce_device(self, keys, m: int, was_unknown, first_issuer_hour, stream=None):
+        self._check(self._lib.ctmr_reduce_device(self._h, capi.ptr(keys), m, capi.ptr(was_unknown),
+                                                 capi.ptr(first_issuer_hour), stream))
+
+    def process_device(self, batch: capi.DevBatch, out: capi.DevOut, stream=None):
+        self._check(self._lib.ctmr_process_device(self._h, C.byref(batch), C.byref(out), stream))
+
+    def partition_keys_device(self, keys, n: int, world: int, keys_by_owner, src_pos, owner_counts, stream=None):
+        self._check(self._lib.ctmr_partition_keys_device(self._h, capi.ptr(keys), n, world, capi.ptr(keys_by_owner),
+                                                         capi.ptr(src_pos), capi.ptr(owner_counts), stream))
+
+    def scatter_bits_device(self, was_unknown, first, src_pos, m: int, was_unknown_dst, first_dst, stream=None):
+        self._check(self._lib.ctmr_scatter_bits_device(self._h, capi.ptr(was_unknown), capi.ptr(first), capi.ptr(src_pos), m,
+                                                       capi.ptr(was_unknown_dst), capi.ptr(first_dst), stream))
+
+    def read_histogram_device(self, counts_dst, n_slots: int, status_dst=None, stream=None):
+        self._check(self._lib.ctmr_read_histogram_device(self._h, capi.ptr(counts_dst), n_slots, capi.ptr(status_dst), stream))
+
+    def reset_device(self, stream=None):
+        self._check(self._lib.ctmr_reset_device(self._h, stream))
+
+    def check_device(self, stream=None):
+        self._check(self._lib.ctmr_check_device(self._h, stream))
+
+    # ------------------------------------------------------------------ reducers' read side
+    def get_known_certificates(self, exp_hour: int, issuer_digest: bytes) -> KnownCertificatesView:
+        return KnownCertificatesView(self, exp_hour, issuer_digest)
+
+    def issuer_counts(self) -> dict:
+        """{Issuer.ID digest (32 bytes): number of unique certificates} for every registered issuer."""
+        n = C.c_size_t(self._lib.ctmr_issuer_count(self._h))
+        cap = max(int(n.value), 1)
+        dig = np.zeros((cap, 32), np.uint8)
+        cnt = np.zeros(cap, np.uint64)
+        self._check(self._lib.ctmr_issuer_counts(self._h, capi.ptr(dig), capi.ptr(cnt), C.byref(n)))
+        return {bytes(dig[i]): int(cnt[i]) for i in range(n.value)}
+
+    def status_counters(self) -> np.ndarray:
+        out = np.zeros(capi.ST_COUNT, np.uint64)
+        self._check(self._lib.ctmr_status_counters(self._h, capi.ptr(out)))
+        return out
+
+    def table_stats(self):
+        used, cap = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.ctmr_table_stats(self._h, C.byref(used), C.byref(cap)))
+        return used.value, cap.value
+
+
+# ---------------------------------------------------------------------- synthetic corpus (bench/test tooling)
+def synth_issuers(cfg: capi.SynthCfg):
+    """DER of the synthetic CA certificates (host side), (blob u8, offsets u64[n_issuers+1])."""
+    L = capi.load()
+    offsets = np.zeros(cfg.n_issuers + 1, np.uint64)
+    total = L.ctmr_synth_issuers_host(C.byref(cfg), capi.ptr(offsets), None, 0)
+    blob = np.zeros(total, np.uint8)
+    L.ctmr_synth_issuers_host(C.byref(cfg), capi.ptr(offsets), capi.ptr(blob), total)
+    return blob, offsets
+
+
+def synth_corpus_device(cfg: capi.SynthCfg, first: int, n: int, device, want_issuer_idx=True):
+    """Generate entries [first, first+n) in HBM: (blob u8, offsets i64-as-u64 [n+1], issuer_idx i32-as-u32 [n])."""
+    import torch
+
+    L = capi.load()
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        total = C.c_uint64(0)
+        rc = L.ctmr_synth_offsets_device(C.byref(cfg), first, n, offsets.data_ptr(), C.byref(total), stream)
+        if rc:
+            raise CtmrError(rc, "ctmr_synth_offsets_device")
+        blob = torch.empty(total.value + 64, dtype=torch.uint8, device=dev)  # readable past the end, 16-byte rounding
+        idx = torch.empty(n, dtype=torch.int32, device=dev) if want_issuer_idx else None
+        rc = L.ctmr_synth_write_device(C.byref(cfg), first, n, offsets.data_ptr(), blob.data_ptr(),
+                                       idx.data_ptr() if idx is not None else None, stream)
+        if rc:
+            raise CtmrError(rc, "ctmr_synth_write_device")
+        torch.cuda.synchronize(dev)
+    return blob, offsets, idx, int(total.value)

@@ -1,0 +1,228 @@
+/*
+ * ctmr.h -- C ABI of the B200-native CT-entry map/reduce hot path (libctmr.so).
+ *
+ * This is the drop-in boundary for ONE path of jcjones/ct-mapreduce (@739eda2): the per-entry
+ * worker and its two reducers.  A Go host binds these entry points with cgo (INTEGRATION.md shows
+ * the stub) and calls them in place of the loop body of
+ *     (*LogSyncEngine).insertCTWorker        cmd/ct-fetch/ct-fetch.go:191-245
+ *     certIsFilteredOut                      cmd/ct-fetch/ct-fetch.go:44-70
+ *     (*FilesystemDatabase).Store            storage/filesystemdatabase.go:158-211
+ *     (*KnownCertificates).WasUnknown/Count  storage/knowncertificates.go:38-63
+ *     (*IssuerMetadata).Accumulate (the seenExpDateBefore bit)  storage/issuermetadata.go:92-108
+ *     NewIssuer/Issuer.ID, NewSerial, NewExpDateFromTime        storage/types.go:109-130,171-178,339-346
+ * while storage.StorageBackend, storage.RemoteCache and storage.CertDatabase
+ * (storage/types.go:46-102) stay byte-identical on the Go side.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; no C++ or torch types; no exceptions cross the ABI.
+ *   - functions return 0 (CTMR_OK) or a negative CTMR_E_* batch-level error; the text is
+ *     available from ctmr_last_error(ctx) until the next call on that ctx.
+ *   - per-entry problems are never return codes: they are status[i] (CTMR_ST_*), exactly like the
+ *     reference's log-and-continue (ct-fetch.go:206-209,223-225,230-232).
+ *   - the caller owns every input and output buffer; the library never keeps a caller pointer
+ *     past return (cgo rule).  Device state lives in an opaque ctmr_ctx.
+ *   - one ctmr_ctx per GPU, calls on a ctx are serialised by the caller; batches are ordered:
+ *     every entry of call k precedes every entry of call k+1 for first-seen semantics.
+ *   - there is no CPU fallback: without a CUDA device ctmr_create fails with CTMR_E_NO_DEVICE.
+ */
+#ifndef CTMR_H
+#define CTMR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTMR_ABI_VERSION 1
+
+/* ---- batch-level return codes ------------------------------------------------------------ */
+enum {
+    CTMR_OK = 0,
+    CTMR_E_INVALID = -1,          /* bad argument */
+    CTMR_E_CUDA = -2,             /* CUDA runtime error (text in ctmr_last_error) */
+    CTMR_E_NOMEM = -3,            /* host or device allocation failed */
+    CTMR_E_TABLE_FULL = -4,       /* known-certificate table exhausted (cf. Redis OOM, rediscache.go:61-63) */
+    CTMR_E_TOO_MANY_ISSUERS = -5, /* more distinct issuers than config.max_issuers */
+    CTMR_E_NO_DEVICE = -6,        /* no usable CUDA device: the product path has no CPU fallback */
+    CTMR_E_BATCH_TOO_LARGE = -7   /* exceeds config.max_batch_* */
+};
+
+/* ---- per-entry status -------------------------------------------------------------------- */
+enum {
+    CTMR_ST_OK = 0,               /* reached Store (counted by insertCTWorker.Inserted, ct-fetch.go:235) */
+    CTMR_ST_PARSE_ERR = 1,        /* "Problem decoding certificate", ct-fetch.go:206-209 */
+    CTMR_ST_FILTER_CA = 2,        /* certIsFilteredOut.CA, ct-fetch.go:47-50 */
+    CTMR_ST_FILTER_EXPIRED = 3,   /* certIsFilteredOut.expired, ct-fetch.go:52-55 */
+    CTMR_ST_FILTER_CN = 4,        /* certIsFilteredOut.cn-filtered, ct-fetch.go:57-68 */
+    CTMR_ST_NO_ISSUER = 5,        /* len(Chain) < 1, ct-fetch.go:215-219 */
+    CTMR_ST_ISSUER_PARSE_ERR = 6, /* "Problem decoding issuing certificate", ct-fetch.go:221-225 */
+    CTMR_ST_SERIAL_TOO_LONG = 7,  /* serial INTEGER longer than CTMR_MAX_SERIAL octets (documented limit) */
+    CTMR_ST__COUNT = 8
+};
+
+#define CTMR_MAX_SERIAL 39u            /* octets of raw serial a key record holds (RFC 5280 allows 20) */
+#define CTMR_ISSUER_NONE 0xFFFFFFFFu   /* issuer_idx value for "entry has no chain" */
+#define CTMR_ISSUER_BAD 0xFFFFFFFEu    /* dense index of an issuer certificate that failed to parse */
+
+/* config.flags */
+#define CTMR_F_NO_FINGERPRINT 1u /* skip SHA-256(leaf DER); the reference itself never computes it */
+
+typedef struct ctmr_ctx ctmr_ctx;
+
+typedef struct ctmr_config {
+    uint32_t struct_size;        /* sizeof(ctmr_config), for ABI evolution */
+    int32_t device;              /* CUDA device ordinal */
+    uint64_t table_capacity;     /* known-certificate slots (64 B each), rounded up to a power of two */
+    uint64_t max_batch_entries;  /* ceiling for one ctmr_process_batch call (sizes device staging); 0 = 1<<20 */
+    uint64_t max_batch_bytes;    /* ceiling for the leaf blob of one call; 0 = 2 KiB * max_batch_entries */
+    uint32_t max_issuers;        /* distinct issuers over the ctx lifetime; 0 = 65536 */
+    uint32_t pair_capacity_log2; /* (issuer, exp-hour) first-seen table, log2 slots; 0 = 24 */
+    const uint8_t* issuer_cn_filter; /* raw config value issuerCNFilter (config/config.go:193): split on ',' */
+    uint32_t issuer_cn_filter_len;   /*   without trimming, HasPrefix on raw CN bytes (ct-fetch.go:57-63)      */
+    uint32_t log_expired_entries;    /* config logExpiredEntries (config/config.go:188) */
+    uint32_t flags;                  /* CTMR_F_* */
+    uint32_t reserved;
+} ctmr_config;
+
+/* Caller-allocated per-entry outputs, each [n]; any pointer may be NULL to skip that copy-back. */
+typedef struct ctmr_out {
+    uint8_t* status;            /* CTMR_ST_* */
+    uint8_t* sha256;            /* [n][32] SHA-256 of the leaf DER (crypto/sha256.Sum256(cert.Raw)) */
+    int64_t* exp_hour;          /* floor(NotAfter/3600 s): NewExpDateFromTime, storage/types.go:339-346 */
+    uint32_t* serial_off;       /* raw serial content octets (NewSerial, storage/types.go:171-178):   */
+    uint32_t* serial_len;       /*   offset inside the entry's DER, and length                          */
+    uint8_t* was_unknown;       /* KnownCertificates.WasUnknown result, storage/knowncertificates.go:38-55 */
+    uint8_t* first_issuer_hour; /* 1 iff Accumulate would return seenExpDateBefore == false (issuermetadata.go:95-108) */
+} ctmr_out;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+uint32_t ctmr_abi_version(void);
+int ctmr_create(const ctmr_config* cfg, ctmr_ctx** out);      /* replaces GetConfiguredStorage wiring, engine/engine.go:19-48 */
+void ctmr_destroy(ctmr_ctx* ctx);
+const char* ctmr_last_error(ctmr_ctx* ctx);                   /* ctx may be NULL: error of the last failed ctmr_create */
+
+/* Pinned host memory for batch packing (the Go batcher packs entries straight into it). */
+void* ctmr_host_alloc(size_t bytes);
+void ctmr_host_free(void* p);
+
+/* ---- issuers ------------------------------------------------------------------------------ */
+/* Parses n issuer certificates (x509.ParseCertificate(Chain[0]), ct-fetch.go:221), computes
+ * Issuer.ID() digests (SHA-256 of RawSubjectPublicKeyInfo, storage/types.go:124-130,155-159) on the
+ * GPU and assigns ctx-lifetime dense indices in order of first appearance.  HOST buffers.
+ * dense_idx_out[k] = dense index, or CTMR_ISSUER_BAD when certificate k does not parse. */
+int ctmr_register_issuers(ctmr_ctx* ctx, const uint8_t* issuer_blob, const uint64_t* issuer_offsets /* [n+1] */,
+                          uint32_t n, uint32_t* dense_idx_out);
+/* digest (32 octets) of a dense index; base64url of it is Issuer.ID() */
+int ctmr_issuer_digest(ctmr_ctx* ctx, uint32_t dense_idx, uint8_t digest_out[32]);
+uint32_t ctmr_issuer_count(ctmr_ctx* ctx);
+
+/* ---- the hot path, HOST buffers (what the Go shim calls) ----------------------------------- */
+/* One call = one batch drained from entryChan (ct-fetch.go:132,191).  blob holds the n leaf DERs
+ * back to back (entry i = blob[offsets[i] .. offsets[i+1])); issuer_* hold the batch's distinct
+ * Chain[0] certificates and issuer_idx[i] selects one (CTMR_ISSUER_NONE = no chain).
+ * now_unix_ns replaces time.Now() at ct-fetch.go:52.  Copies host->device, runs the kernels,
+ * copies the requested outputs back; synchronous. */
+int ctmr_process_batch(ctmr_ctx* ctx, const uint8_t* blob, const uint64_t* offsets /* [n+1] */, uint64_t n,
+                       const uint8_t* issuer_blob, const uint64_t* issuer_offsets /* [n_issuers+1] */,
+                       uint32_t n_issuers, const uint32_t* issuer_idx /* [n] */, int64_t now_unix_ns,
+                       ctmr_out* out);
+
+/* ---- reducers' read side ------------------------------------------------------------------- */
+/* Per-issuer unique-certificate counts = sum over expDates of KnownCertificates.Count()
+ * (cmd/storage-statistics/storage-statistics.go:44-53).  *n in: capacity, out: issuers written. */
+int ctmr_issuer_counts(ctmr_ctx* ctx, uint8_t* digests /* [cap][32] */, uint64_t* counts /* [cap] */, size_t* n);
+/* SetCardinality("serials::<expDate>::<issuer>"), storage/knowncertificates.go:57-63 */
+int ctmr_set_cardinality(ctmr_ctx* ctx, int64_t exp_hour, const uint8_t issuer_digest[32], uint64_t* count_out);
+/* entries per status since create, indexed by CTMR_ST_* (the certIsFilteredOut.* / Inserted counters) */
+int ctmr_status_counters(ctmr_ctx* ctx, uint64_t out[CTMR_ST__COUNT]);
+int ctmr_table_stats(ctmr_ctx* ctx, uint64_t* slots_used, uint64_t* capacity);
+
+/* ---- device-resident entry points ---------------------------------------------------------- */
+/* Same path with every buffer already in HBM on ctx's device (benchmarks, multi-GPU orchestration,
+ * hosts that receive entries by GPUDirect).  `stream` is a cudaStream_t passed as void*; NULL =
+ * the ctx's own stream.  Asynchronous: the caller synchronises the stream. */
+
+/* 64-byte key record: what WasUnknown is keyed on: expDate hour, issuer, raw serial. */
+typedef struct ctmr_key {
+    uint64_t index;      /* global entry index: lowest index of equal keys wins "was unknown" */
+    int32_t exp_hour;
+    uint32_t issuer;     /* dense issuer index */
+    uint8_t serial_len;
+    uint8_t serial[CTMR_MAX_SERIAL]; /* zero padded */
+    uint32_t valid;      /* 1 when the entry reached Store (status OK) */
+    uint32_t pad;
+} ctmr_key;
+
+typedef struct ctmr_dev_batch {
+    const uint8_t* blob;        /* device; readable up to blob_bytes rounded up to 16 */
+    uint64_t blob_bytes;
+    const uint64_t* offsets;    /* device [n+1] */
+    uint64_t n;
+    const uint32_t* issuer_idx; /* device [n]; NULL = every entry has no chain */
+    const uint32_t* issuer_map; /* device [*]: batch-local -> dense index, or NULL when issuer_idx is dense */
+    uint32_t issuer_map_len;
+    uint32_t reserved;
+    uint64_t first_index;       /* global index of entry 0 */
+    int64_t now_unix_ns;
+} ctmr_dev_batch;
+
+typedef struct ctmr_dev_out { /* device pointers, each [n]; NULL = not produced */
+    uint8_t* status;
+    uint8_t* sha256;
+    int64_t* exp_hour;
+    uint32_t* serial_off;
+    uint32_t* serial_len;
+    uint8_t* was_unknown;
+    uint8_t* first_issuer_hour;
+    ctmr_key* keys; /* [n] key records (valid=0 for entries that did not reach Store) */
+} ctmr_dev_out;
+
+/* map half: DER walk + filter + SHA-256 -> status, exp_hour, serial span, fingerprint, key records */
+int ctmr_map_device(ctmr_ctx* ctx, const ctmr_dev_batch* batch, const ctmr_dev_out* out, void* stream);
+/* reduce half over m key records in any order: insert, resolve lowest-index-wins, per-issuer counts */
+int ctmr_reduce_device(ctmr_ctx* ctx, const ctmr_key* keys, uint64_t m, uint8_t* was_unknown /* [m] */,
+                       uint8_t* first_issuer_hour /* [m] */, void* stream);
+/* map + reduce on one GPU */
+int ctmr_process_device(ctmr_ctx* ctx, const ctmr_dev_batch* batch, const ctmr_dev_out* out, void* stream);
+
+/* multi-GPU key routing: owner(key) = hash(exp_hour, issuer) mod world, i.e. one
+ * Redis set lives on one GPU.  Counting-sort the valid keys by owner. */
+int ctmr_partition_keys_device(ctmr_ctx* ctx, const ctmr_key* keys, uint64_t n, uint32_t world,
+                               ctmr_key* keys_by_owner /* [n] */, uint32_t* src_pos /* [n] */,
+                               uint64_t* owner_counts /* device [world] */, void* stream);
+/* scatter routed-back result bits to entry order: dst[src_pos[j]] = bits[j], j < m */
+int ctmr_scatter_bits_device(ctmr_ctx* ctx, const uint8_t* was_unknown, const uint8_t* first_issuer_hour,
+                             const uint32_t* src_pos, uint64_t m, uint8_t* was_unknown_dst,
+                             uint8_t* first_issuer_hour_dst, void* stream);
+/* copy the per-issuer histogram (uint64 [n_slots], dense index order) and the status counters
+ * (uint64 [CTMR_ST__COUNT]) into device buffers, e.g. for one ncclAllReduce(sum) per chunk */
+int ctmr_read_histogram_device(ctmr_ctx* ctx, uint64_t* counts_dst, uint32_t n_slots, uint64_t* status_dst,
+                               void* stream);
+/* forget everything: known-certificate table, first-seen pairs, per-issuer and status counters
+ * (the issuer registry is kept).  The analogue of FLUSHDB on the reference's Redis. */
+int ctmr_reset_device(ctmr_ctx* ctx, void* stream);
+/* fails with CTMR_E_TABLE_FULL / CTMR_E_CUDA if any asynchronous launch since the last check failed */
+int ctmr_check_device(ctmr_ctx* ctx, void* stream);
+
+/* ---- synthetic corpus on the device (bench/test tooling; ctmr_synth.h) ---------------------- */
+struct ctmr_synth_cfg;
+/* pass 1: offsets[0..n] (device) of entries [first, first+n); returns total bytes via *total_bytes */
+int ctmr_synth_offsets_device(const struct ctmr_synth_cfg* cfg, uint64_t first, uint64_t n, uint64_t* offsets,
+                              uint64_t* total_bytes, void* stream);
+/* pass 2: write the DER bytes and (optionally) the issuer index of each entry */
+int ctmr_synth_write_device(const struct ctmr_synth_cfg* cfg, uint64_t first, uint64_t n, const uint64_t* offsets,
+                            uint8_t* blob, uint32_t* issuer_idx, void* stream);
+/* generator-side truth for size-independent checks: cert id, notAfter, basicConstraints mode */
+int ctmr_synth_truth_device(const struct ctmr_synth_cfg* cfg, uint64_t first, uint64_t n, uint64_t* cert_id,
+                            int64_t* not_after, uint8_t* bc_mode, void* stream);
+
+/* host-side: DER of the n_issuers synthetic CA certificates; returns total bytes, fills
+ * offsets[0..n_issuers]; writes bytes when blob != NULL and cap suffices */
+uint64_t ctmr_synth_issuers_host(const struct ctmr_synth_cfg* cfg, uint64_t* offsets, uint8_t* blob, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTMR_H */

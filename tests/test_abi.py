@@ -1,0 +1,93 @@
+"""The C-ABI shared library: loads, exports every symbol include/ctmr.h declares, and refuses to
+run without a GPU (no CPU fallback).  No compute calls here -- those are the -m gpu tests."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ct_mapreduce_b200 import build, capi
+    build.build()
+    return capi.load()
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "ctmr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctmr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = _declared_functions()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ctmr.h but not exported by libctmr.so"
+
+
+def test_python_binding_covers_header(lib):
+    from ct_mapreduce_b200 import capi
+    assert sorted(capi.EXPORTS) == _declared_functions()
+
+
+def test_abi_version(lib):
+    assert lib.ctmr_abi_version() == 1
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """ctypes mirrors vs. the header itself, measured by compiling a probe with gcc."""
+    import subprocess
+    from ct_mapreduce_b200 import capi
+    src = tmp_path / "probe.c"
+    src.write_text('#include "include/ctmr.h"\n#include "ct_mapreduce_b200/csrc/ctmr_synth.h"\n#include <stdio.h>\n'
+                   '#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ctmr_config), sizeof(ctmr_out),'
+                   'sizeof(ctmr_dev_batch), sizeof(ctmr_dev_out), sizeof(ctmr_synth_cfg), sizeof(ctmr_key),'
+                   'offsetof(ctmr_key, serial), offsetof(ctmr_key, valid));return 0;}\n')
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", ROOT, str(src), "-o", str(exe)], check=True, cwd=ROOT)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(capi.Config), C.sizeof(capi.Out), C.sizeof(capi.DevBatch), C.sizeof(capi.DevOut),
+                   C.sizeof(capi.SynthCfg), capi.KEY_DTYPE.itemsize, capi.KEY_DTYPE.fields["serial"][1],
+                   capi.KEY_DTYPE.fields["valid"][1]]
+    assert capi.KEY_DTYPE.itemsize == 64
+
+
+def test_library_is_blackwell_native():
+    """The shipped .so carries sm_100a SASS with the TMA bulk-copy instruction in the map kernel."""
+    import shutil
+    import subprocess
+    from ct_mapreduce_b200 import capi
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not installed")
+    elf = subprocess.run([cuobjdump, "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run([cuobjdump, "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS" in sass
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ct_mapreduce_b200 import capi, engine
+    with pytest.raises(capi.CtmrError) as ei:
+        engine.GpuCertDatabase()
+    assert ei.value.code == capi.E_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under ct_mapreduce_b200/ or include/ may reference it."""
+    bad = []
+    for base in ("ct_mapreduce_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"\boracle\b", txt) and "ora_" in txt or "import oracle" in txt or "from oracle" in txt:
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

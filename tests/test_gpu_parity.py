@@ -1,0 +1,225 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs -- bit-exact for every output (fingerprints, membership bits, per-issuer counts).
+Marked gpu: they run on the B200 box."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import NOW_NS, NOW_SEC, README_FILTER, pack
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("status", "exp_hour", "serial_off", "serial_len", "was_unknown", "first_issuer_hour")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from ct_mapreduce_b200 import build, engine
+    build.build()
+    return engine
+
+
+def assert_same(r_gpu, r_ora, sha=True):
+    for f in FIELDS:
+        a, b = getattr(r_gpu, f), getattr(r_ora, f)
+        if f in ("exp_hour", "serial_off", "serial_len"):  # defined where the leaf parsed
+            m = r_ora.status != 1
+            a, b = a[m], b[m]
+        bad = np.nonzero(a != b)[0]
+        assert bad.size == 0, (f, bad[:10], a[bad[:10]], b[bad[:10]])
+    if sha:
+        bad = np.nonzero((r_gpu.sha256 != r_ora.sha256).any(axis=1))[0]
+        assert bad.size == 0, ("sha256", bad[:10])
+
+
+def run_both(eng, ora, blob, offs, iblob, ioffs, idx, now_ns=NOW_NS, flt=README_FILTER, log_expired=False, **kw):
+    odb = ora.DB(flt, log_expired)
+    r_ora = odb.process(blob, offs, iblob, ioffs, idx, now_ns)
+    with eng.GpuCertDatabase(issuer_cn_filter=flt, log_expired_entries=log_expired, table_capacity=1 << 18, **kw) as db:
+        r_gpu = db.store_batch(blob, offs, iblob, ioffs, idx, now_ns)
+        counts = db.issuer_counts()
+        sc = db.status_counters()
+    return r_gpu, r_ora, counts, odb, sc
+
+
+def test_config1_10k_uniform(eng, ora):
+    """BASELINE.json configs[0]: 10k synthetic ~1.5 KB certs, full map + both reducers."""
+    n = 10000
+    cfg = ora.synth_cfg(n)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    r_gpu, r_ora, counts, odb, sc = run_both(eng, ora, blob, offs, iblob, ioffs, idx)
+    assert_same(r_gpu, r_ora)
+    oc = odb.issuer_counts()
+    assert {k: v for k, v in counts.items() if v} == oc
+    assert np.array_equal(sc, odb.filter_counters())
+    # independent check of the fingerprints
+    for i in (0, 1, 17, n - 1):
+        assert r_gpu.sha256[i].tobytes() == hashlib.sha256(blob[offs[i]:offs[i + 1]].tobytes()).digest()
+
+
+def test_mixed_sizes_with_duplicates(eng, ora):
+    """configs[4] shape: 512 B-8 KB, every certificate twice, 256 issuers."""
+    n = 12000
+    cfg = ora.synth_cfg(n, len_mode=1, len_lo=512, len_hi=8192, dup_mode=1)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    r_gpu, r_ora, counts, odb, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, flt=b"")
+    assert_same(r_gpu, r_ora)
+    ok = r_ora.status == 0
+    assert int(r_gpu.was_unknown.sum()) * 2 == int(ok.sum())  # every kept certificate has exactly one twin
+    assert {k: v for k, v in counts.items() if v} == odb.issuer_counts()
+
+
+def test_persistence_across_batches(eng, ora):
+    """The known-certificate set outlives a batch: later batches see earlier entries (Redis set)."""
+    n = 6000
+    cfg = ora.synth_cfg(n, dup_mode=1)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    odb = ora.DB(README_FILTER, False)
+    with eng.GpuCertDatabase(issuer_cn_filter=README_FILTER, table_capacity=1 << 16) as db:
+        cuts = [0, 1000, 1001, 3500, n]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            sub_offs = offs[a:b + 1]
+            r_o = odb.process(blob, sub_offs, iblob, ioffs, idx[a:b], NOW_NS)
+            r_g = db.store_batch(blob, sub_offs, iblob, ioffs, idx[a:b], NOW_NS)
+            assert_same(r_g, r_o)
+        assert {k: v for k, v in db.issuer_counts().items() if v} == odb.issuer_counts()
+        # KnownCertificates.Count for a few (expDate, issuer) sets
+        r_all = ora.DB(README_FILTER, False).process(blob, offs, iblob, ioffs, idx, NOW_NS)
+        dense = db.register_issuers(iblob, ioffs)
+        for i in np.nonzero(r_all.status == 0)[0][:25]:
+            dig = db.issuer_digest(int(dense[idx[i]]))
+            assert db.get_known_certificates(int(r_all.exp_hour[i]), dig).count() == odb.set_cardinality(int(r_all.exp_hour[i]), dig)
+
+
+def test_pipeline_sub_batches(eng, ora):
+    """Force the host path through many pipeline stages; results must not depend on the staging."""
+    n = 9000
+    cfg = ora.synth_cfg(n, dup_mode=1)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    r_gpu, r_ora, counts, odb, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, max_batch_entries=700)
+    assert_same(r_gpu, r_ora)
+    r_gpu2, _, _, _, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, max_batch_entries=4096, max_batch_bytes=1 << 20)
+    assert_same(r_gpu2, r_ora)
+
+
+def test_reference_fixtures(eng, ora, golden):
+    """The reference's embedded PEMs through the GPU path (types_test.go:21-39, filesystemdatabase_test.go:17-64)."""
+    lz, ca, real = golden["kLeadingZeroes"]["der"], golden["kEmptySPKI"]["der"], golden["kRealSPKI"]["der"]
+    ders = [lz, lz, ca, real, lz]
+    blob, offs = pack(ders)
+    iblob, ioffs = pack([ca, real])
+    idx = np.array([0, 0, 0, 1, 0xFFFFFFFF], np.uint32)
+    before = (golden["kLeadingZeroes"]["not_after_unix"] - 10) * 10**9
+    r_gpu, r_ora, counts, odb, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, now_ns=before, flt=b"")
+    assert_same(r_gpu, r_ora)
+    assert list(r_gpu.status) == [0, 0, 2, 2, 5]
+    for i, d in enumerate(ders):
+        assert r_gpu.sha256[i].tobytes().hex() == hashlib.sha256(d).hexdigest()
+    assert r_gpu.sha256[0].tobytes().hex() == golden["kLeadingZeroes"]["sha256_der"]
+    s0 = int(r_gpu.serial_off[0])
+    assert lz[s0:s0 + int(r_gpu.serial_len[0])].hex() == "00aa"  # types_test.go:93
+    # Issuer.ID of the CA = golden digest (types.go:124-130)
+    import base64
+    (dig, cnt), = [(k, v) for k, v in counts.items() if v]
+    assert base64.urlsafe_b64encode(dig).decode() == golden["kEmptySPKI"]["issuer_id_of_own_spki"] and cnt == 1
+
+
+def test_filter_variants(eng, ora):
+    n = 3000
+    cfg = ora.synth_cfg(n)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    for flt, le in ((b"", False), (b"", True), (b"Let's Encrypt", False), (b"Let's Encrypt,ISRG", True),
+                    (b"x,", False), (b" ISRG Root X1,Synth Trust Services CA 3,Let's Encrypt Authority X12", False),
+                    (b",", False), (b"Z" * 100, False)):
+        r_gpu, r_ora, _, _, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, flt=flt, log_expired=le)
+        assert_same(r_gpu, r_ora, sha=False)
+    # now with a fractional part: NotAfter.Before(now) strictness
+    r_gpu, r_ora, _, _, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, now_ns=NOW_NS + 1, flt=b"")
+    assert_same(r_gpu, r_ora, sha=False)
+
+
+def _mutations(der, rng):
+    out = [der[:-1], der + b"\x00", der[:len(der) // 2], b"", b"\x30", b"\x30\x80", b"\x30\x84\xff\xff\xff\xff", der[:4]]
+    for _ in range(60):
+        b = bytearray(der)
+        for _ in range(rng.integers(1, 4)):
+            b[rng.integers(0, min(len(b), 420))] = rng.integers(0, 256)
+        out.append(bytes(b))
+    return out
+
+
+def test_malformed_inputs_are_safe_and_agree(eng, ora, golden):
+    """Truncated / corrupted DER: never a crash, status agrees with the oracle, the fingerprint is
+    still SHA-256 of the raw bytes (edge cases: empty record, ragged sizes, 1-byte records)."""
+    rng = np.random.default_rng(7)
+    cfg = ora.synth_cfg(64)
+    blob0, offs0, _ = ora.synth_corpus(cfg, 0, 8)
+    ders = []
+    for i in range(8):
+        ders += _mutations(blob0[offs0[i]:offs0[i + 1]].tobytes(), rng)
+    ders += _mutations(golden["kRealSPKI"]["der"], rng)
+    blob, offs = pack(ders)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    bad_issuer = iblob[ioffs[3]:ioffs[4]].tobytes()[:-7]
+    iblob2, ioffs2 = pack([iblob[ioffs[0]:ioffs[1]].tobytes(), bad_issuer])
+    idx = (np.arange(len(ders)) % 3).astype(np.uint32)
+    idx[idx == 2] = 0xFFFFFFFF
+    r_gpu, r_ora, _, _, _ = run_both(eng, ora, blob, offs, iblob2, ioffs2, idx, flt=b"", log_expired=True)
+    assert_same(r_gpu, r_ora)
+    assert set(np.unique(r_gpu.status)) >= {0, 1, 5, 6}
+    for i, d in enumerate(ders):
+        assert r_gpu.sha256[i].tobytes() == hashlib.sha256(d).digest(), i
+
+
+def test_padding_boundaries_every_length(eng, ora):
+    """Fingerprint of records of every length 0..300 at every 16-byte misalignment (SHA-256 padding
+    edges at 55/56/63/64 and the 256-byte streaming chunk edge)."""
+    rng = np.random.default_rng(3)
+    ders = [rng.integers(0, 256, size=L, dtype=np.uint8).tobytes() for L in range(0, 301)]
+    ders += [rng.integers(0, 256, size=L, dtype=np.uint8).tobytes() for L in (511, 512, 513, 767, 768, 1023, 1024, 1025, 4095, 4096, 8191, 8192, 20000)]
+    blob, offs = pack(ders)
+    with eng.GpuCertDatabase(table_capacity=1 << 12) as db:
+        r = db.store_batch(blob, offs, None, None, None, NOW_NS)
+    assert (r.status == 1).all()
+    for i, d in enumerate(ders):
+        assert r.sha256[i].tobytes() == hashlib.sha256(d).digest(), len(d)
+
+
+def test_empty_batch_and_no_issuers(eng, ora):
+    with eng.GpuCertDatabase(table_capacity=1 << 12) as db:
+        r = db.store_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64), None, None, None, NOW_NS)
+        assert r.status.size == 0
+        cfg = ora.synth_cfg(100)
+        blob, offs, idx = ora.synth_corpus(cfg, 0, 100)
+        r = db.store_batch(blob, offs, None, None, None, NOW_NS)  # no chain at all
+        exp = ora.DB(b"", False).process(blob, offs, np.zeros(0, np.uint8), np.zeros(1, np.uint64),
+                                         np.full(100, 0xFFFFFFFF, np.uint32), NOW_NS)
+        assert np.array_equal(r.status, exp.status) and not r.was_unknown.any()
+
+
+def test_table_full_is_reported(eng, ora):
+    from ct_mapreduce_b200 import capi
+    n = 20000
+    cfg = ora.synth_cfg(n)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    with eng.GpuCertDatabase(table_capacity=4096) as db:
+        with pytest.raises(capi.CtmrError) as ei:
+            db.store_batch(blob, offs, iblob, ioffs, idx, NOW_NS)
+        assert ei.value.code == capi.E_TABLE_FULL
+
+
+def test_no_fingerprint_flag(eng, ora):
+    from ct_mapreduce_b200 import capi
+    n = 2000
+    cfg = ora.synth_cfg(n, dup_mode=1)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    r_gpu, r_ora, _, _, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, flags=capi.F_NO_FINGERPRINT)
+    assert_same(r_gpu, r_ora, sha=False)
