@@ -33,16 +33,29 @@ struct Sha256State {
     }
 };
 
-#define CTMR_SHA_ROUND(a, b, c, d, e, f, g, h, k, w)                 \
-    do {                                                             \
-        uint32_t t1_ = (h) + bsig1(e) + ch((e), (f), (g)) + (k) + (w); \
-        uint32_t t2_ = bsig0(a) + maj((a), (b), (c));                \
-        (d) += t1_;                                                  \
-        (h) = t1_ + t2_;                                             \
+// Additions are steered onto the FMA pipe: `mad.lo.u32 d, a, 1, b` assembles to IMAD.IADD, which
+// issues on the (otherwise idle) FMA datapath, while rotations (SHF) and the boolean functions
+// (LOP3) can only run on the ALU datapath.  ncu on the all-IADD3 version showed the ALU pipe as the
+// binding unit (61 % busy, FMA 4 %); per 64-byte block this split leaves 1088 ALU + 464 FMA
+// instructions instead of ~1440 ALU (profiles/, DESIGN.md "K_map").
+__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+#define CTMR_SHA_ROUND(a, b, c, d, e, f, g, h, k, w)                     \
+    do {                                                                 \
+        uint32_t t1_ = (h) + (w) + (k); /* one IADD3 with the immediate */ \
+        t1_ = fadd(fadd(t1_, bsig1(e)), ch((e), (f), (g)));              \
+        uint32_t t2_ = fadd(bsig0(a), maj((a), (b), (c)));               \
+        (d) = fadd((d), t1_);                                            \
+        (h) = fadd(t1_, t2_);                                            \
     } while (0)
 
-#define CTMR_SHA_SCHED(w, i) \
-    ((w)[(i) & 15] += ssig1((w)[((i) - 2) & 15]) + (w)[((i) - 7) & 15] + ssig0((w)[((i) - 15) & 15]))
+#define CTMR_SHA_SCHED(w, i)                                                                          \
+    ((w)[(i) & 15] = fadd(fadd(fadd((w)[(i) & 15], ssig1((w)[((i) - 2) & 15])), (w)[((i) - 7) & 15]), \
+                          ssig0((w)[((i) - 15) & 15])))
 
 // One 64-byte block; w[16] holds the big-endian message words and is clobbered.
 __device__ __forceinline__ void sha256_compress(Sha256State& s, uint32_t (&w)[16]) {
@@ -70,6 +83,44 @@ __device__ __forceinline__ void sha256_compress(Sha256State& s, uint32_t (&w)[16
         CTMR_SHA_ROUND(d, e, f, g, h, a, b, c, K[i + 5], w[(i + 5) & 15]);
         CTMR_SHA_ROUND(c, d, e, f, g, h, a, b, K[i + 6], w[(i + 6) & 15]);
         CTMR_SHA_ROUND(b, c, d, e, f, g, h, a, K[i + 7], w[(i + 7) & 15]);
+    }
+    s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+}
+
+// Same compression with the 64 rounds rolled into 4 passes of 16 (round constants from the constant
+// bank instead of immediates).  ~7 KB of code instead of ~26 KB: ncu charged 20 % of warp time to
+// "no_instruction" (instruction-cache misses) on the fully unrolled body once 8-16 desynchronised
+// warps per SM walk it at different offsets.
+__constant__ uint32_t kSha256K[64] = {
+    0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+    0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+    0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+    0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+    0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+    0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+    0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+    0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+
+__device__ __forceinline__ void sha256_compress_rolled(Sha256State& s, uint32_t (&w)[16]) {
+    uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        if (it != 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) CTMR_SHA_SCHED(w, j);
+        }
+        const uint32_t* kp = kSha256K + 16 * it;
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+            CTMR_SHA_ROUND(a, b, c, d, e, f, g, h, kp[j + 0], w[j + 0]);
+            CTMR_SHA_ROUND(h, a, b, c, d, e, f, g, kp[j + 1], w[j + 1]);
+            CTMR_SHA_ROUND(g, h, a, b, c, d, e, f, kp[j + 2], w[j + 2]);
+            CTMR_SHA_ROUND(f, g, h, a, b, c, d, e, kp[j + 3], w[j + 3]);
+            CTMR_SHA_ROUND(e, f, g, h, a, b, c, d, kp[j + 4], w[j + 4]);
+            CTMR_SHA_ROUND(d, e, f, g, h, a, b, c, kp[j + 5], w[j + 5]);
+            CTMR_SHA_ROUND(c, d, e, f, g, h, a, b, kp[j + 6], w[j + 6]);
+            CTMR_SHA_ROUND(b, c, d, e, f, g, h, a, kp[j + 7], w[j + 7]);
+        }
     }
     s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }

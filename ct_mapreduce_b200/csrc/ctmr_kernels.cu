@@ -19,6 +19,8 @@
 #include "ctmr_kernels.cuh"
 
 #include "ctmr_device.cuh"
+#include "ctmr_stream.cuh"
+#include <cstdlib>
 
 namespace ctmr {
 
@@ -272,20 +274,246 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {
-    if (p.n == 0) return cudaSuccess;
-    // shape of the persistent grid; the defaults are the measured best (DESIGN.md "K_map tuning")
+cudaError_t launch_map_v1(const MapParams& p, int sm_count, cudaStream_t s) {
     static const int warps = env_int("CTMR_MAP_WARPS", 4);
-    static const int chunk = env_int("CTMR_MAP_CHUNK", 256);
     static const int cps = env_int("CTMR_MAP_CTAS_PER_SM", 0);
-    if (chunk == 512) {
-        if (warps == 2) return launch_map_t<2, 512>(p, sm_count, cps ? cps : 3, s);
-        if (warps == 6) return launch_map_t<6, 512>(p, sm_count, cps ? cps : 1, s);
-        return launch_map_t<4, 512>(p, sm_count, cps ? cps : 1, s);
-    }
     if (warps == 8) return launch_map_t<8, 256>(p, sm_count, cps ? cps : 1, s);
-    if (warps == 2) return launch_map_t<2, 256>(p, sm_count, cps ? cps : 6, s);
     return launch_map_t<4, 256>(p, sm_count, cps ? cps : 3, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_map v2: single-pass streaming map.  The DER walker (ctmr_stream.cuh) and the SHA-256 loop both
+// eat from the same per-lane shared-memory window; global memory is touched once per byte, by
+// asynchronous copies only.  Chunks overlap by kOverlap bytes so that a TLV header (and the small
+// values the walker captures) never straddles a refill.
+//   LOADER 0: per-lane cp.async 16-byte copies (LDGSTS) + commit/wait groups -- no barrier at all
+//   LOADER 1: per-lane TMA bulk copy (UBLKCP) + per-warp mbarrier pair
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int WARPS, int CHUNK, int LOADER, int ROLLED = 0>
+struct StreamCfg {
+    static constexpr int kOverlap = 64;
+    static constexpr int kSlot = kOverlap + CHUNK + 16;
+    static constexpr int kWarpBytes = 2 * 32 * kSlot;
+    static constexpr int kBlocksPerChunk = CHUNK / 64;
+    static constexpr int kPieces = kSlot / 16;
+    static constexpr size_t kSmem = (size_t)WARPS * kWarpBytes + (LOADER == 1 ? (size_t)WARPS * 2 * sizeof(uint64_t) : 0);
+};
+
+struct GlobalBytes {
+    const uint8_t* d;
+    __device__ __forceinline__ uint32_t operator()(uint32_t x) const { return __ldg(d + x); }
+};
+
+template <int WARPS, int CHUNK, int LOADER, int ROLLED>
+__global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_constant__ MapParams p) {
+    using Cfg = StreamCfg<WARPS, CHUNK, LOADER>;
+    constexpr uint32_t OV = Cfg::kOverlap;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* my_slots = smem + (size_t)warp * Cfg::kWarpBytes + (size_t)lane * Cfg::kSlot;  // stage s at + s*32*kSlot
+    const uint32_t slot0 = smem_u32(my_slots), slot1 = slot0 + 32 * Cfg::kSlot;
+    uint32_t bar0 = 0, bar1 = 0, parity = 0;
+    if (LOADER == 1) {
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * Cfg::kWarpBytes) + warp * 2;
+        bar0 = smem_u32(&bars[0]);
+        bar1 = smem_u32(&bars[1]);
+        if (lane == 0) {
+            mbar_init(bar0, 32);
+            mbar_init(bar1, 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
+
+    const uint64_t ngroups = (p.n + 31) >> 5;
+    const bool want_sha = p.sha256 != nullptr;
+    for (uint64_t g = (uint64_t)blockIdx.x * WARPS + warp; g < ngroups; g += (uint64_t)gridDim.x * WARPS) {
+        const uint64_t e = g * 32 + lane;
+        const bool act = e < p.n;
+        uint64_t off = 0, end = 0;
+        if (act) {
+            off = p.offsets[e];
+            end = p.offsets[e + 1];
+        }
+        const bool bad_span = !act || end < off || end > p.blob_bytes || end - off > 0x7fffffffull;
+        const uint32_t L = bad_span ? 0u : (uint32_t)(end - off);
+        const uint8_t* d = p.blob + off;
+        const uint64_t addr = reinterpret_cast<uint64_t>(d);
+        const uint32_t m = (uint32_t)(addr & 15u);
+        const uint8_t* src_base = reinterpret_cast<const uint8_t*>(addr & ~15ull);
+        const uint32_t nfull = L >> 6;
+        const uint32_t nb = want_sha && act ? nfull + 1u + ((L & 63u) >= 56u ? 1u : 0u) : 0u;
+        const uint32_t ndata = act ? (L + CHUNK - 1) / CHUNK : 0u;
+        uint32_t nch = (nb + Cfg::kBlocksPerChunk - 1) / Cfg::kBlocksPerChunk;
+        nch = nch > ndata ? nch : ndata;                    // without SHA the walker alone drives the stream
+        if (act && nch == 0u) nch = 1u;                     // empty record: one step so that the walker reports the error
+        uint32_t iters = warp_max_u32(nch);
+        iters = iters < 2u ? 2u : iters;
+
+        // chunk c stages record bytes [c*CHUNK - OV, c*CHUNK + CHUNK) (chunk 0: [0, CHUNK)); byte x sits
+        // at slot offset m + OV + x - c*CHUNK in every chunk
+        auto issue = [&](uint32_t c) {
+            const uint32_t slot = (c & 1u) ? slot1 : slot0;
+            uint32_t bytes = 0, dst = slot;
+            const uint8_t* src = src_base;
+            if (c < ndata) {
+                const uint32_t db = min((uint32_t)CHUNK, L - c * CHUNK);
+                if (c == 0u) {
+                    bytes = (m + db + 15u) & ~15u;
+                    dst = slot + OV;
+                } else {
+                    bytes = (m + OV + db + 15u) & ~15u;
+                    src = src_base + (size_t)c * CHUNK - OV;
+                }
+            }
+            if (LOADER == 1) {
+                const uint32_t bar = (c & 1u) ? bar1 : bar0;
+                if (bytes) {
+                    mbar_arrive_expect_tx(bar, bytes);
+                    bulk_g2s(dst, src, bytes, bar);
+                } else {
+                    mbar_arrive(bar);
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t j = 0; j < bytes; j += 16u) cp_async16(dst + j, src + j);
+                cp_async_commit();
+            }
+        };
+        issue(0);
+        issue(1);
+
+        Walker w;
+        w.init();
+        uint32_t* key_words = (p.keys && act) ? reinterpret_cast<uint32_t*>(p.keys + e) + 4 : nullptr;
+        const GlobalBytes far{d};
+        Sha256State st;
+        st.init();
+        const uint32_t sel = 0x0123u + 0x1111u * (m & 3u);
+
+        for (uint32_t c = 0; c < iters; ++c) {
+            const uint32_t s = c & 1u;
+            if (LOADER == 1) {
+                mbar_wait(s ? bar1 : bar0, (parity >> s) & 1u);
+                parity ^= 1u << s;
+            } else {
+                cp_async_wait<1>();  // everything but the newest group (chunk c+1) has landed
+            }
+            if (c < nch) {
+                const uint8_t* slot = my_slots + (size_t)s * 32 * Cfg::kSlot;
+                // ---- map: resume the TLV walk over the newly staged bytes
+                if (act && w.st < W_DONE) {
+                    const uint32_t avail = min((c + 1u) * CHUNK, L);
+                    const SmemWindow rd{(s ? slot1 : slot0) + m + OV - c * CHUNK};
+                    walk_advance(w, rd, far, bad_span ? 0u : avail, L, p.filter, key_words);
+                }
+                // ---- fingerprint: the chunk's 64-byte blocks
+#pragma unroll 1
+                for (uint32_t bb = 0; bb < (uint32_t)Cfg::kBlocksPerChunk; ++bb) {
+                    const uint32_t b = c * Cfg::kBlocksPerChunk + bb;
+                    if (b >= nb) break;
+                    const uint32_t* sw = reinterpret_cast<const uint32_t*>(slot) + ((m + OV + 64u * bb) >> 2);
+                    uint32_t x[17], wd[16];
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) x[i] = sw[i];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) wd[i] = __byte_perm(x[i], x[i + 1], sel);
+                    if (b >= nfull) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) wd[i] = sha256_pad_word(wd[i], b * 64u + 4u * i, L);
+                        if (b == nb - 1u) {
+                            wd[14] = L >> 29;
+                            wd[15] = L << 3;
+                        }
+                    }
+                    if (ROLLED) sha256_compress_rolled(st, wd);
+                    else sha256_compress(st, wd);
+                }
+            }
+            if (c + 2u < iters) issue(c + 2u);
+            else if (LOADER == 0) cp_async_commit();  // keep "newest group = the one after chunk c+1" true at the tail
+        }
+        if (LOADER == 0) cp_async_wait<0>();
+
+        // ---- certIsFilteredOut + Store preconditions, in the reference's order
+        if (act) {
+            uint32_t status = CTMR_ST_PARSE_ERR, issuer = CTMR_ISSUER_NONE;
+            int64_t exp_hour = 0;
+            uint32_t serial_off = 0, serial_len = 0;
+            if (w.st == W_DONE) {
+                status = CTMR_ST_OK;
+                serial_off = w.serial_off;
+                serial_len = w.serial_len;
+                exp_hour = w.not_after >= 0 ? w.not_after / 3600 : -((-w.not_after + 3599) / 3600);
+                if ((w.flags & (WF_BC_VALID | WF_IS_CA)) == (WF_BC_VALID | WF_IS_CA)) {
+                    status = CTMR_ST_FILTER_CA;
+                } else if (!p.filter.log_expired &&
+                           (w.not_after < p.now_sec || (w.not_after == p.now_sec && p.now_frac_nonzero))) {
+                    status = CTMR_ST_FILTER_EXPIRED;
+                } else if (p.filter.filter_nonempty) {
+                    // CommonName "" (no CN attribute) matches only an empty prefix
+                    bool keep = (w.flags & WF_HAS_CN) ? (w.flags & WF_CN_MATCH) != 0 : false;
+                    if (!(w.flags & WF_HAS_CN))
+                        for (uint32_t q = 0; q < p.filter.n_prefix; ++q) keep |= p.filter.off[q + 1] == p.filter.off[q];
+                    if (!keep) status = CTMR_ST_FILTER_CN;
+                }
+                if (status == CTMR_ST_OK) {
+                    uint32_t k = p.issuer_idx ? p.issuer_idx[e] : CTMR_ISSUER_NONE;
+                    if (k != CTMR_ISSUER_NONE && p.issuer_map) k = k < p.issuer_map_len ? p.issuer_map[k] : CTMR_ISSUER_NONE;
+                    issuer = k;
+                    if (k == CTMR_ISSUER_NONE) status = CTMR_ST_NO_ISSUER;
+                    else if (k == CTMR_ISSUER_BAD) status = CTMR_ST_ISSUER_PARSE_ERR;
+                    else if (serial_len > CTMR_MAX_SERIAL) status = CTMR_ST_SERIAL_TOO_LONG;
+                }
+            }
+            if (p.status) p.status[e] = (uint8_t)status;
+            if (p.exp_hour) p.exp_hour[e] = exp_hour;
+            if (p.serial_off) p.serial_off[e] = serial_off;
+            if (p.serial_len) p.serial_len[e] = serial_len;
+            if (p.keys) {
+                const bool valid = status == CTMR_ST_OK;
+                const uint64_t gi = p.first_index + e;
+                uint4* kr = reinterpret_cast<uint4*>(p.keys + e);
+                kr[0] = make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)(int32_t)exp_hour, valid ? issuer : 0u);
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(kr) + 14) = make_uint2(valid ? 1u : 0u, 0u);
+            }
+            if (want_sha) {
+                uint4* o = reinterpret_cast<uint4*>(p.sha256 + e * 32);
+                o[0] = make_uint4(__byte_perm(st.h[0], 0, 0x0123), __byte_perm(st.h[1], 0, 0x0123),
+                                  __byte_perm(st.h[2], 0, 0x0123), __byte_perm(st.h[3], 0, 0x0123));
+                o[1] = make_uint4(__byte_perm(st.h[4], 0, 0x0123), __byte_perm(st.h[5], 0, 0x0123),
+                                  __byte_perm(st.h[6], 0, 0x0123), __byte_perm(st.h[7], 0, 0x0123));
+            }
+            if (p.status_counts) {
+                const uint32_t peers = __match_any_sync(__activemask(), status);
+                if ((uint32_t)lane == (uint32_t)__ffs(peers) - 1u)
+                    atomicAdd(p.status_counts + status, (unsigned long long)__popc(peers));
+            }
+        }
+    }
+}
+
+template <int WARPS, int CHUNK, int LOADER, int ROLLED = 0>
+static cudaError_t launch_stream_t(const MapParams& p, int sm_count, int ctas_per_sm, cudaStream_t s) {
+    using Cfg = StreamCfg<WARPS, CHUNK, LOADER>;
+    auto kern = map_stream_kernel<WARPS, CHUNK, LOADER, ROLLED>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if (err != cudaSuccess) return err;
+    const uint64_t ngroups = (p.n + 31) / 32;
+    uint64_t ctas = (uint64_t)sm_count * ctas_per_sm;
+    const uint64_t need = (ngroups + WARPS - 1) / WARPS;
+    if (need < ctas) ctas = need ? need : 1;
+    kern<<<(unsigned)ctas, WARPS * 32, Cfg::kSmem, s>>>(p);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -568,6 +796,34 @@ cudaError_t launch_scatter_bits(const uint8_t* a, const uint8_t* b, const uint32
     if (!m) return cudaSuccess;
     scatter_bits_kernel<<<blocks_for(m, 256), 256, 0, s>>>(a, b, src_pos, m, a_dst, b_dst);
     return cudaGetLastError();
+}
+
+// Shape of the persistent grid.  Defaults = the measured best (DESIGN.md "K_map tuning"); the
+// environment overrides exist for the A/B runs recorded under profiles/.
+cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {
+    if (p.n == 0) return cudaSuccess;
+    static const int variant = env_int("CTMR_MAP_VARIANT", 2);   // 1: v1 (global-memory walk), 2: streaming walk
+    static const int loader = env_int("CTMR_MAP_LOADER", 0);     // 0: cp.async (LDGSTS), 1: TMA bulk copy
+    static const int warps = env_int("CTMR_MAP_WARPS", 4);
+    static const int chunk = env_int("CTMR_MAP_CHUNK", 256);
+    static const int cps = env_int("CTMR_MAP_CTAS_PER_SM", 0);
+    if (variant == 1) return launch_map_v1(p, sm_count, s);
+    if (loader == 1) {
+        if (chunk == 128) return launch_stream_t<4, 128, 1>(p, sm_count, cps ? cps : 4, s);
+        return launch_stream_t<4, 256, 1>(p, sm_count, cps ? cps : 2, s);
+    }
+    static const int rolled = env_int("CTMR_MAP_ROLLED", 0);
+    if (rolled) {
+        if (chunk == 128) return launch_stream_t<8, 128, 0, 1>(p, sm_count, cps ? cps : 2, s);
+        if (warps == 4) return launch_stream_t<4, 256, 0, 1>(p, sm_count, cps ? cps : 2, s);
+        return launch_stream_t<8, 256, 0, 1>(p, sm_count, cps ? cps : 1, s);
+    }
+    if (chunk == 128) {
+        if (warps == 8) return launch_stream_t<8, 128, 0>(p, sm_count, cps ? cps : 2, s);
+        return launch_stream_t<4, 128, 0>(p, sm_count, cps ? cps : 4, s);
+    }
+    if (warps == 8) return launch_stream_t<8, 256, 0>(p, sm_count, cps ? cps : 1, s);
+    return launch_stream_t<4, 256, 0>(p, sm_count, cps ? cps : 2, s);
 }
 
 }  // namespace ctmr

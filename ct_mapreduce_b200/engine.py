@@ -216,7 +216,7 @@ def synth_corpus_device(cfg: capi.SynthCfg, first: int, n: int, device, want_iss
     L = capi.load()
     dev = torch.device(device)
     with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = torch.cuda.current_stream(dev).cuda_stream or 1  # 0x1 = cudaStreamLegacy
         offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
         total = C.c_uint64(0)
         rc = L.ctmr_synth_offsets_device(C.byref(cfg), first, n, offsets.data_ptr(), C.byref(total), stream)
