@@ -171,6 +171,7 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
     int64_t sec = ns >= 0 ? ns / 1000000000LL : -((-ns + 999999999LL) / 1000000000LL);
     p.now_sec = sec;
     p.now_frac_nonzero = (ns - sec * 1000000000LL) != 0;
+    p.one = 1;
     p.status = o->status;
     p.sha256 = (c->flags & CTMR_F_NO_FINGERPRINT) ? nullptr : o->sha256;
     p.exp_hour = o->exp_hour;

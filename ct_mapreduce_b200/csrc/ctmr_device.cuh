@@ -33,32 +33,33 @@ struct Sha256State {
     }
 };
 
-// Additions are steered onto the FMA pipe: `mad.lo.u32 d, a, 1, b` assembles to IMAD.IADD, which
-// issues on the (otherwise idle) FMA datapath, while rotations (SHF) and the boolean functions
-// (LOP3) can only run on the ALU datapath.  ncu on the all-IADD3 version showed the ALU pipe as the
-// binding unit (61 % busy, FMA 4 %); per 64-byte block this split leaves 1088 ALU + 464 FMA
-// instructions instead of ~1440 ALU (profiles/, DESIGN.md "K_map").
-__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b) {
+// Additions are steered onto the FMA pipe.  Rotations (SHF) and the boolean functions (LOP3) can
+// only issue on the ALU datapath, and ncu showed that datapath as the binding unit (ALU 61-74 %
+// busy, FMA 4-6 %) because ptxas turns every add into IADD3 -- including `mad.lo x, 1, y`, which
+// it folds back.  Multiplying by a run-time 1 (a kernel parameter it cannot fold) keeps a genuine
+// IMAD, which issues on the otherwise idle FMA datapath: per 64-byte block ~1090 ALU + ~460 FMA
+// instructions instead of ~1290 ALU + 160 FMA (profiles/, DESIGN.md "K_map").
+__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t one) {
     uint32_t d;
-    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
     return d;
 }
 
 #define CTMR_SHA_ROUND(a, b, c, d, e, f, g, h, k, w)                     \
     do {                                                                 \
-        uint32_t t1_ = (h) + (w) + (k); /* one IADD3 with the immediate */ \
-        t1_ = fadd(fadd(t1_, bsig1(e)), ch((e), (f), (g)));              \
-        uint32_t t2_ = fadd(bsig0(a), maj((a), (b), (c)));               \
-        (d) = fadd((d), t1_);                                            \
-        (h) = fadd(t1_, t2_);                                            \
+        uint32_t t1_ = (h) + (w) + (k); /* one IADD3 with the constant */  \
+        t1_ = fadd(fadd(bsig1(e), t1_, one), ch((e), (f), (g)), one);    \
+        uint32_t t2_ = fadd(bsig0(a), maj((a), (b), (c)), one);          \
+        (d) = fadd((d), t1_, one);                                       \
+        (h) = fadd(t1_, t2_, one);                                       \
     } while (0)
 
-#define CTMR_SHA_SCHED(w, i)                                                                          \
-    ((w)[(i) & 15] = fadd(fadd(fadd((w)[(i) & 15], ssig1((w)[((i) - 2) & 15])), (w)[((i) - 7) & 15]), \
-                          ssig0((w)[((i) - 15) & 15])))
+#define CTMR_SHA_SCHED(w, i)                                                                                    \
+    ((w)[(i) & 15] = fadd(fadd(fadd(ssig1((w)[((i) - 2) & 15]), (w)[(i) & 15], one), (w)[((i) - 7) & 15], one), \
+                          ssig0((w)[((i) - 15) & 15]), one))
 
 // One 64-byte block; w[16] holds the big-endian message words and is clobbered.
-__device__ __forceinline__ void sha256_compress(Sha256State& s, uint32_t (&w)[16]) {
+__device__ __forceinline__ void sha256_compress(Sha256State& s, uint32_t (&w)[16], const uint32_t one) {
     constexpr uint32_t K[64] = {
         0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
         0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
@@ -101,7 +102,7 @@ __constant__ uint32_t kSha256K[64] = {
     0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
     0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
 
-__device__ __forceinline__ void sha256_compress_rolled(Sha256State& s, uint32_t (&w)[16]) {
+__device__ __forceinline__ void sha256_compress_rolled(Sha256State& s, uint32_t (&w)[16], const uint32_t one) {
     uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {
@@ -151,7 +152,7 @@ __device__ inline void sha256_global(const uint8_t* __restrict__ p, uint32_t len
             w[i] = sha256_pad_word(v, q, len);
         }
         if (b == nb - 1) { w[14] = 0; w[15] = len * 8u; }
-        sha256_compress(s, w);
+        sha256_compress_rolled(s, w, 1u);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) out[i] = s.h[i];

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(WARPS * 32) map_kernel(const __grid_constant__
                                 w[15] = L << 3;
                             }
                         }
-                        sha256_compress(st, w);
+                        sha256_compress(st, w, p.one);
                     }
                 }
                 if (c + 2u < iters) issue(c + 2u);
@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
         Sha256State st;
         st.init();
         const uint32_t sel = 0x0123u + 0x1111u * (m & 3u);
+        const uint32_t one = p.one;
 
         for (uint32_t c = 0; c < iters; ++c) {
             const uint32_t s = c & 1u;
@@ -435,8 +436,8 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
                             wd[15] = L << 3;
                         }
                     }
-                    if (ROLLED) sha256_compress_rolled(st, wd);
-                    else sha256_compress(st, wd);
+                    if (ROLLED) sha256_compress_rolled(st, wd, one);
+                    else sha256_compress(st, wd, one);
                 }
             }
             if (c + 2u < iters) issue(c + 2u);
@@ -804,15 +805,15 @@ cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {
     if (p.n == 0) return cudaSuccess;
     static const int variant = env_int("CTMR_MAP_VARIANT", 2);   // 1: v1 (global-memory walk), 2: streaming walk
     static const int loader = env_int("CTMR_MAP_LOADER", 0);     // 0: cp.async (LDGSTS), 1: TMA bulk copy
-    static const int warps = env_int("CTMR_MAP_WARPS", 4);
-    static const int chunk = env_int("CTMR_MAP_CHUNK", 256);
+    static const int warps = env_int("CTMR_MAP_WARPS", 8);
+    static const int chunk = env_int("CTMR_MAP_CHUNK", 128);
     static const int cps = env_int("CTMR_MAP_CTAS_PER_SM", 0);
     if (variant == 1) return launch_map_v1(p, sm_count, s);
     if (loader == 1) {
         if (chunk == 128) return launch_stream_t<4, 128, 1>(p, sm_count, cps ? cps : 4, s);
         return launch_stream_t<4, 256, 1>(p, sm_count, cps ? cps : 2, s);
     }
-    static const int rolled = env_int("CTMR_MAP_ROLLED", 0);
+    static const int rolled = env_int("CTMR_MAP_ROLLED", 1);
     if (rolled) {
         if (chunk == 128) return launch_stream_t<8, 128, 0, 1>(p, sm_count, cps ? cps : 2, s);
         if (warps == 4) return launch_stream_t<4, 256, 0, 1>(p, sm_count, cps ? cps : 2, s);

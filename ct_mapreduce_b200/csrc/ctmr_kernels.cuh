@@ -55,7 +55,7 @@ struct MapParams {
     uint64_t first_index;
     int64_t now_sec;
     uint32_t now_frac_nonzero;
-    uint32_t pad2;
+    uint32_t one;  // always 1: a multiplier ptxas cannot fold (see fadd in ctmr_device.cuh)
     uint8_t* status;
     uint8_t* sha256;
     int64_t* exp_hour;

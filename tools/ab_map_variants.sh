@@ -7,11 +7,9 @@ while read -r v; do
   [ -z "$v" ] && continue
   echo "== $v"; env $v $B 2>&1 | python -c "$P" || env $v $B 2>&1 | tail -5
 done <<'LIST'
-CTMR_MAP_VARIANT=1
 CTMR_MAP_VARIANT=2 CTMR_MAP_LOADER=0 CTMR_MAP_WARPS=8 CTMR_MAP_CHUNK=256 CTMR_MAP_ROLLED=0
 CTMR_MAP_VARIANT=2 CTMR_MAP_LOADER=0 CTMR_MAP_WARPS=8 CTMR_MAP_CHUNK=256 CTMR_MAP_ROLLED=1
-CTMR_MAP_VARIANT=2 CTMR_MAP_LOADER=0 CTMR_MAP_WARPS=4 CTMR_MAP_CHUNK=256 CTMR_MAP_ROLLED=1
 CTMR_MAP_VARIANT=2 CTMR_MAP_LOADER=0 CTMR_MAP_WARPS=8 CTMR_MAP_CHUNK=128 CTMR_MAP_ROLLED=0
 CTMR_MAP_VARIANT=2 CTMR_MAP_LOADER=0 CTMR_MAP_WARPS=8 CTMR_MAP_CHUNK=128 CTMR_MAP_ROLLED=1
-CTMR_MAP_VARIANT=2 CTMR_MAP_LOADER=1 CTMR_MAP_CHUNK=256
+CTMR_MAP_VARIANT=2 CTMR_MAP_LOADER=1 CTMR_MAP_CHUNK=128
 LIST
