@@ -152,11 +152,15 @@ CTMR_HD uint8_t* ctmr_emit(uint8_t* p, const uint8_t* s, uint32_t n) {
 }
 
 CTMR_HD uint32_t ctmr_fmt_u32(char* dst, uint32_t v) {
-    char tmp[10];
-    uint32_t n = 0;
-    do { tmp[n++] = (char)('0' + v % 10u); v /= 10u; } while (v);
-    for (uint32_t i = 0; i < n; ++i) dst[i] = tmp[n - 1 - i];
-    return n;
+    /* digits are written straight into dst (no scratch array: nvcc 12.9 overlapped a local scratch
+     * buffer with the caller's string buffer here, caught by tests/test_gpu_parity.py) */
+    uint32_t nd = 1;
+    for (uint32_t t = v; t >= 10u; t /= 10u) ++nd;
+    for (uint32_t i = nd; i-- > 0u;) {
+        dst[i] = (char)('0' + v % 10u);
+        v /= 10u;
+    }
+    return nd;
 }
 
 CTMR_HD uint32_t ctmr_cat(char* dst, uint32_t at, const char* s) {

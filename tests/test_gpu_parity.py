@@ -223,3 +223,24 @@ def test_no_fingerprint_flag(eng, ora):
     iblob, ioffs = ora.synth_issuers(cfg)
     r_gpu, r_ora, _, _, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, flags=capi.F_NO_FINGERPRINT)
     assert_same(r_gpu, r_ora, sha=False)
+
+
+def test_device_generator_matches_host_generator(eng, ora):
+    """The bench corpus is generated in HBM; the CPU arm regenerates it on the host: same bytes."""
+    import torch
+    from ct_mapreduce_b200 import capi
+    for kw in (dict(), dict(len_mode=1, len_lo=512, len_hi=8192, dup_mode=1), dict(len_mode=1, len_lo=512, len_hi=4096, dup_mode=1)):
+        n, first = 3000, 1234
+        cfg_o = ora.synth_cfg(50000, **kw)
+        cfg_g = capi.synth_cfg(50000, **kw)
+        blob, offs, idx = ora.synth_corpus(cfg_o, first, n)
+        dblob, doffs, didx, total = eng.synth_corpus_device(cfg_g, first, n, "cuda:0")
+        assert total == int(offs[-1])
+        assert np.array_equal(doffs.cpu().numpy().astype(np.uint64), offs)
+        assert np.array_equal(didx.cpu().numpy().astype(np.uint32), idx)
+        got = dblob[:total].cpu().numpy()
+        bad = np.nonzero(got != blob)[0]
+        assert bad.size == 0, (kw, bad[:10])
+        iblob_o, ioffs_o = ora.synth_issuers(cfg_o)
+        iblob_g, ioffs_g = eng.synth_issuers(cfg_g)
+        assert np.array_equal(iblob_o, iblob_g) and np.array_equal(ioffs_o, ioffs_g)
