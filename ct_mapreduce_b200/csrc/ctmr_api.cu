@@ -4,6 +4,7 @@
 // without a CUDA device ctmr_create fails.
 #include <array>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -39,6 +40,8 @@ struct Stage {
     ctmr_key* keys = nullptr;
     uint32_t* slot_of = nullptr;
     uint32_t* pair_slot = nullptr;
+    uint32_t* order = nullptr;
+    unsigned int* len_hist = nullptr;
 };
 
 }  // namespace
@@ -66,6 +69,10 @@ struct ctmr_ctx {
     uint32_t* pair_scratch = nullptr;
     uint8_t* bits_scratch = nullptr;
     uint64_t scratch_cap = 0;
+    uint32_t* order_scratch = nullptr;  // length-bucketed order of the device entry points
+    uint64_t order_cap = 0;
+    unsigned int* len_hist = nullptr;
+    bool bucket_by_length = true;
     unsigned long long* small_dev = nullptr;  // [64] cursors / cardinality result
     std::string err;
 };
@@ -137,6 +144,8 @@ int ensure_stages(ctmr_ctx* c) {
         CU(c, cudaMalloc(&s.keys, E * sizeof(ctmr_key)));
         CU(c, cudaMalloc(&s.slot_of, E * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.pair_slot, E * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.order, E * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.len_hist, 256 * sizeof(unsigned int)));
     }
     c->stages_ready = true;
     return CTMR_OK;
@@ -156,7 +165,7 @@ int ensure_scratch(ctmr_ctx* c, uint64_t n) {
     return CTMR_OK;
 }
 
-void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, MapParams& p) {
+void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, MapParams& p, int counter_slot = 3) {
     std::memset(&p, 0, sizeof p);
     p.blob = b->blob;
     p.blob_bytes = b->blob_bytes;
@@ -179,6 +188,7 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
     p.serial_len = o->serial_len;
     p.keys = o->keys;
     p.status_counts = c->st.status_counts;
+    p.work_counter = c->small_dev + 84 + counter_slot;  // one per pipeline stage + one for the device entry points
     p.filter = c->filter;
 }
 
@@ -270,6 +280,7 @@ int ctmr_create(const ctmr_config* cfg, ctmr_ctx** out) {
                                               : kStageEntries;
     const uint64_t want_bytes = cfg->max_batch_bytes ? cfg->max_batch_bytes : c->stage_entries * 2048ull;
     c->stage_bytes = want_bytes < kStageBytes ? want_bytes : kStageBytes;
+    if (const char* ev = getenv("CTMR_BUCKET_BY_LENGTH")) c->bucket_by_length = atoi(ev) != 0;
     CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
     *out = c;
@@ -283,13 +294,13 @@ void ctmr_destroy(ctmr_ctx* c) {
     for (Stage& s : c->stages) {
         cudaFree(s.blob); cudaFree(s.offsets); cudaFree(s.issuer_idx); cudaFree(s.status); cudaFree(s.sha);
         cudaFree(s.exp_hour); cudaFree(s.serial_off); cudaFree(s.serial_len); cudaFree(s.was_unknown); cudaFree(s.first);
-        cudaFree(s.keys); cudaFree(s.slot_of); cudaFree(s.pair_slot);
+        cudaFree(s.keys); cudaFree(s.slot_of); cudaFree(s.pair_slot); cudaFree(s.order); cudaFree(s.len_hist);
         if (s.reduced) cudaEventDestroy(s.reduced);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     cudaFree(c->st.table); cudaFree(c->st.pairs); cudaFree(c->st.issuer_counts); cudaFree(c->small_dev);
     cudaFree(c->issuer_map_dev); cudaFree(c->keys_scratch); cudaFree(c->slot_scratch); cudaFree(c->pair_scratch);
-    cudaFree(c->bits_scratch);
+    cudaFree(c->bits_scratch); cudaFree(c->order_scratch); cudaFree(c->len_hist);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -377,7 +388,21 @@ int ctmr_map_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o,
     CU(c, cudaSetDevice(c->device));
     MapParams p;
     fill_map_params(c, b, o, p);
-    CU(c, launch_map(p, c->sm_count, stream ? (cudaStream_t)stream : c->stream));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    if (c->bucket_by_length && b->n > 64) {
+        if (b->n > c->order_cap) {
+            CU(c, cudaDeviceSynchronize());
+            cudaFree(c->order_scratch);
+            c->order_scratch = nullptr;
+            c->order_cap = 0;
+            CU(c, cudaMalloc(&c->order_scratch, b->n * sizeof(uint32_t)));
+            c->order_cap = b->n;
+        }
+        if (!c->len_hist) CU(c, cudaMalloc(&c->len_hist, 256 * sizeof(unsigned int)));
+        CU(c, launch_len_order(b->offsets, b->n, b->blob_bytes, c->len_hist, c->order_scratch, s));
+        p.order = c->order_scratch;
+    }
+    CU(c, launch_map(p, c->sm_count, s));
     return CTMR_OK;
 }
 
@@ -523,7 +548,11 @@ int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets
         dout.serial_len = s.serial_len;
         dout.keys = s.keys;
         MapParams p;
-        fill_map_params(c, &db, &dout, p);
+        fill_map_params(c, &db, &dout, p, sub % kStages);
+        if (c->bucket_by_length && cnt > 64) {
+            CU(c, launch_len_order(s.offsets, cnt, db.blob_bytes, s.len_hist, s.order, s.stream));
+            p.order = s.order;
+        }
         CU(c, launch_map(p, c->sm_count, s.stream));
         if (prev) CU(c, cudaStreamWaitEvent(s.stream, prev, 0));
         CU(c, launch_insert(c->st, s.keys, cnt, s.slot_of, s.stream));
@@ -572,10 +601,10 @@ int ctmr_set_cardinality(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32]
     *out = 0;
     auto it = c->issuer_by_digest.find(std::string(reinterpret_cast<const char*>(digest), 32));
     if (it == c->issuer_by_digest.end() || exp_hour > INT32_MAX || exp_hour < INT32_MIN) return CTMR_OK;
-    CU(c, cudaMemsetAsync(c->small_dev + 32, 0, sizeof(unsigned long long), c->stream));
-    CU(c, launch_cardinality(c->st, (int32_t)exp_hour, it->second, c->small_dev + 32, c->stream));
+    CU(c, cudaMemsetAsync(c->small_dev + 80, 0, sizeof(unsigned long long), c->stream));
+    CU(c, launch_cardinality(c->st, (int32_t)exp_hour, it->second, c->small_dev + 80, c->stream));
     unsigned long long v = 0;
-    CU(c, cudaMemcpyAsync(&v, c->small_dev + 32, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(&v, c->small_dev + 80, sizeof v, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     *out = v;
     return CTMR_OK;

@@ -63,10 +63,14 @@ struct MapParams {
     uint32_t* serial_len;
     ctmr_key* keys;
     unsigned long long* status_counts;
+    unsigned long long* work_counter;  // [1] scratch of the dynamically scheduled map kernel
+    const uint32_t* order;             // [n] length-bucketed processing order (NULL = entry order)
     FilterCfg filter;
 };
 
 cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_len_order(const uint64_t* offsets, uint64_t n, uint64_t blob_bytes, unsigned int* hist256, uint32_t* order,
+                             cudaStream_t s);
 cudaError_t launch_insert(const DeviceState& st, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, cudaStream_t s);
 cudaError_t launch_resolve(const DeviceState& st, const ctmr_key* keys, uint64_t m, const uint32_t* slot_of,
                            uint32_t* pair_slot, uint8_t* was_unknown, cudaStream_t s);
