@@ -73,6 +73,13 @@ struct ctmr_ctx {
     uint64_t order_cap = 0;
     unsigned int* len_hist = nullptr;
     bool bucket_by_length = true;
+    bool fuse_insert = true;
+    // ctmr_process_device pipelines map (stream A) against reduce (stream B) over kSub sub-batches
+    cudaStream_t stream_a = nullptr, stream_b = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join_a = nullptr, ev_join_b = nullptr;
+    cudaEvent_t ev_map0[8] = {}, ev_map1[8] = {}, ev_red1[8] = {};
+    int last_sub = 0;
+    unsigned int* len_hist_sub[8] = {};
     unsigned long long* small_dev = nullptr;  // [64] cursors / cardinality result
     std::string err;
 };
@@ -165,7 +172,8 @@ int ensure_scratch(ctmr_ctx* c, uint64_t n) {
     return CTMR_OK;
 }
 
-void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, MapParams& p, int counter_slot = 3) {
+void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, MapParams& p, int counter_slot = 3,
+                     uint32_t* fused_slot_of = nullptr) {
     std::memset(&p, 0, sizeof p);
     p.blob = b->blob;
     p.blob_bytes = b->blob_bytes;
@@ -181,6 +189,10 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
     p.now_sec = sec;
     p.now_frac_nonzero = (ns - sec * 1000000000LL) != 0;
     p.one = 1;
+    {
+        static const int sh[12] = {2, 13, 22, 6, 11, 25, 7, 18, 3, 17, 19, 10};
+        for (int i = 0; i < 12; ++i) p.rot_mul[i] = 1u << (32 - sh[i]);
+    }
     p.status = o->status;
     p.sha256 = (c->flags & CTMR_F_NO_FINGERPRINT) ? nullptr : o->sha256;
     p.exp_hour = o->exp_hour;
@@ -190,11 +202,17 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
     p.status_counts = c->st.status_counts;
     p.work_counter = c->small_dev + 84 + counter_slot;  // one per pipeline stage + one for the device entry points
     p.filter = c->filter;
+    if (fused_slot_of && p.keys) {  // K_insert fused into K_map (single-GPU paths)
+        p.table = c->st.table;
+        p.table_mask = c->st.table_mask;
+        p.error_flag = c->st.error_flag;
+        p.slot_of = fused_slot_of;
+    }
 }
 
 int reduce_on(ctmr_ctx* c, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, uint32_t* pair_slot, uint8_t* was_unknown,
-              uint8_t* first, cudaStream_t s) {
-    CU(c, launch_insert(c->st, keys, m, slot_of, s));
+              uint8_t* first, cudaStream_t s, bool already_inserted = false) {
+    if (!already_inserted) CU(c, launch_insert(c->st, keys, m, slot_of, s));
     CU(c, launch_resolve(c->st, keys, m, slot_of, pair_slot, was_unknown, s));
     CU(c, launch_resolve_pairs(c->st, keys, m, pair_slot, was_unknown, first, s));
     return CTMR_OK;
@@ -281,6 +299,8 @@ int ctmr_create(const ctmr_config* cfg, ctmr_ctx** out) {
     const uint64_t want_bytes = cfg->max_batch_bytes ? cfg->max_batch_bytes : c->stage_entries * 2048ull;
     c->stage_bytes = want_bytes < kStageBytes ? want_bytes : kStageBytes;
     if (const char* ev = getenv("CTMR_BUCKET_BY_LENGTH")) c->bucket_by_length = atoi(ev) != 0;
+    if (const char* ev = getenv("CTMR_FUSE_INSERT")) c->fuse_insert = atoi(ev) != 0;
+    if (const char* ev = getenv("CTMR_MAP_VARIANT")) if (atoi(ev) != 2) c->fuse_insert = false;  // only the streaming kernel fuses
     CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
     *out = c;
@@ -301,6 +321,17 @@ void ctmr_destroy(ctmr_ctx* c) {
     cudaFree(c->st.table); cudaFree(c->st.pairs); cudaFree(c->st.issuer_counts); cudaFree(c->small_dev);
     cudaFree(c->issuer_map_dev); cudaFree(c->keys_scratch); cudaFree(c->slot_scratch); cudaFree(c->pair_scratch);
     cudaFree(c->bits_scratch); cudaFree(c->order_scratch); cudaFree(c->len_hist);
+    for (int k = 0; k < 8; ++k) {
+        cudaFree(c->len_hist_sub[k]);
+        if (c->ev_map0[k]) cudaEventDestroy(c->ev_map0[k]);
+        if (c->ev_map1[k]) cudaEventDestroy(c->ev_map1[k]);
+        if (c->ev_red1[k]) cudaEventDestroy(c->ev_red1[k]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join_a) cudaEventDestroy(c->ev_join_a);
+    if (c->ev_join_b) cudaEventDestroy(c->ev_join_b);
+    if (c->stream_a) cudaStreamDestroy(c->stream_a);
+    if (c->stream_b) cudaStreamDestroy(c->stream_b);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -418,16 +449,93 @@ int ctmr_reduce_device(ctmr_ctx* c, const ctmr_key* keys, uint64_t m, uint8_t* w
 
 int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, void* stream) {
     if (!c || !b || !o) return fail(c, CTMR_E_INVALID, "bad argument");
+    if (b->n && (!b->blob || !b->offsets)) return fail(c, CTMR_E_INVALID, "null batch buffers");
     CU(c, cudaSetDevice(c->device));
     int rc = ensure_scratch(c, b->n);
     if (rc) return rc;
-    ctmr_dev_out oo = *o;
-    if (!oo.keys) oo.keys = c->keys_scratch;
-    rc = ctmr_map_device(c, b, &oo, stream);
-    if (rc) return rc;
-    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
-    return reduce_on(c, oo.keys, b->n, c->slot_scratch, c->pair_scratch, oo.was_unknown ? oo.was_unknown : c->bits_scratch,
-                     oo.first_issuer_hour ? oo.first_issuer_hour : c->bits_scratch + b->n, s);
+    if (c->bucket_by_length && b->n > c->order_cap) {
+        CU(c, cudaDeviceSynchronize());
+        cudaFree(c->order_scratch);
+        c->order_scratch = nullptr;
+        c->order_cap = 0;
+        CU(c, cudaMalloc(&c->order_scratch, b->n * sizeof(uint32_t)));
+        c->order_cap = b->n;
+    }
+    if (!c->stream_a) {
+        CU(c, cudaStreamCreateWithFlags(&c->stream_a, cudaStreamNonBlocking));
+        CU(c, cudaStreamCreateWithFlags(&c->stream_b, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_join_a, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_join_b, cudaEventDisableTiming));
+        for (int k = 0; k < 8; ++k) {
+            CU(c, cudaEventCreate(&c->ev_map0[k]));
+            CU(c, cudaEventCreate(&c->ev_map1[k]));
+            CU(c, cudaEventCreate(&c->ev_red1[k]));
+            CU(c, cudaMalloc(&c->len_hist_sub[k], 256 * sizeof(unsigned int)));
+        }
+    }
+    cudaStream_t user = stream ? (cudaStream_t)stream : c->stream;
+    // The map half is INT-pipe bound and the reduce half is latency/atomic bound: run sub-batch
+    // k+1's K_map (stream A) while sub-batch k's insert/resolve/pairs run (stream B).
+    const int nsub = b->n >= (1u << 21) ? 4 : (b->n >= (1u << 18) ? 2 : 1);
+    ctmr_key* keys = o->keys ? o->keys : c->keys_scratch;
+    uint8_t* wu = o->was_unknown ? o->was_unknown : c->bits_scratch;
+    uint8_t* fi = o->first_issuer_hour ? o->first_issuer_hour : c->bits_scratch + b->n;
+    CU(c, cudaEventRecord(c->ev_fork, user));
+    CU(c, cudaStreamWaitEvent(c->stream_a, c->ev_fork, 0));
+    CU(c, cudaStreamWaitEvent(c->stream_b, c->ev_fork, 0));
+    for (int k = 0; k < nsub; ++k) {
+        const uint64_t lo = b->n * k / nsub, hi = b->n * (k + 1) / nsub, cnt = hi - lo;
+        ctmr_dev_batch sb = *b;
+        sb.offsets = b->offsets + lo;
+        sb.n = cnt;
+        sb.issuer_idx = b->issuer_idx ? b->issuer_idx + lo : nullptr;
+        sb.first_index = b->first_index + lo;
+        ctmr_dev_out so{};
+        so.status = o->status ? o->status + lo : nullptr;
+        so.sha256 = o->sha256 ? o->sha256 + lo * 32 : nullptr;
+        so.exp_hour = o->exp_hour ? o->exp_hour + lo : nullptr;
+        so.serial_off = o->serial_off ? o->serial_off + lo : nullptr;
+        so.serial_len = o->serial_len ? o->serial_len + lo : nullptr;
+        so.keys = keys + lo;
+        MapParams p;
+        fill_map_params(c, &sb, &so, p, 3, c->fuse_insert ? c->slot_scratch + lo : nullptr);
+        CU(c, cudaEventRecord(c->ev_map0[k], c->stream_a));
+        if (c->bucket_by_length && cnt > 64) {
+            CU(c, launch_len_order(sb.offsets, cnt, sb.blob_bytes, c->len_hist_sub[k], c->order_scratch + lo, c->stream_a));
+            p.order = c->order_scratch + lo;
+        }
+        CU(c, launch_map(p, c->sm_count, c->stream_a));
+        CU(c, cudaEventRecord(c->ev_map1[k], c->stream_a));
+        CU(c, cudaStreamWaitEvent(c->stream_b, c->ev_map1[k], 0));
+        rc = reduce_on(c, keys + lo, cnt, c->slot_scratch + lo, c->pair_scratch + lo, wu + lo, fi + lo, c->stream_b,
+                       c->fuse_insert);
+        if (rc) return rc;
+        CU(c, cudaEventRecord(c->ev_red1[k], c->stream_b));
+    }
+    c->last_sub = nsub;
+    CU(c, cudaEventRecord(c->ev_join_a, c->stream_a));
+    CU(c, cudaEventRecord(c->ev_join_b, c->stream_b));
+    CU(c, cudaStreamWaitEvent(user, c->ev_join_a, 0));
+    CU(c, cudaStreamWaitEvent(user, c->ev_join_b, 0));
+    return CTMR_OK;
+}
+
+/* CUDA-event timings of the last ctmr_process_device call (after the caller synchronised):
+ * map_ms = sum of the K_map stage durations on their stream, total_ms = first map start -> last reduce end */
+int ctmr_profile_last(ctmr_ctx* c, float* map_ms, float* total_ms) {
+    if (!c || c->last_sub <= 0) return fail(c, CTMR_E_INVALID, "no ctmr_process_device call to report");
+    CU(c, cudaSetDevice(c->device));
+    float m = 0.f, t = 0.f;
+    for (int k = 0; k < c->last_sub; ++k) {
+        float d = 0.f;
+        CU(c, cudaEventElapsedTime(&d, c->ev_map0[k], c->ev_map1[k]));
+        m += d;
+    }
+    CU(c, cudaEventElapsedTime(&t, c->ev_map0[0], c->ev_red1[c->last_sub - 1]));
+    if (map_ms) *map_ms = m;
+    if (total_ms) *total_ms = t;
+    return CTMR_OK;
 }
 
 int ctmr_partition_keys_device(ctmr_ctx* c, const ctmr_key* keys, uint64_t n, uint32_t world, ctmr_key* by_owner,
@@ -548,14 +656,15 @@ int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets
         dout.serial_len = s.serial_len;
         dout.keys = s.keys;
         MapParams p;
-        fill_map_params(c, &db, &dout, p, sub % kStages);
+        fill_map_params(c, &db, &dout, p, sub % kStages, c->fuse_insert ? s.slot_of : nullptr);
         if (c->bucket_by_length && cnt > 64) {
             CU(c, launch_len_order(s.offsets, cnt, db.blob_bytes, s.len_hist, s.order, s.stream));
             p.order = s.order;
         }
         CU(c, launch_map(p, c->sm_count, s.stream));
+        // inserts commute (atomicMax on ~index); only RESOLVE must see every earlier entry inserted
+        if (!c->fuse_insert) CU(c, launch_insert(c->st, s.keys, cnt, s.slot_of, s.stream));
         if (prev) CU(c, cudaStreamWaitEvent(s.stream, prev, 0));
-        CU(c, launch_insert(c->st, s.keys, cnt, s.slot_of, s.stream));
         CU(c, launch_resolve(c->st, s.keys, cnt, s.slot_of, s.pair_slot, s.was_unknown, s.stream));
         CU(c, cudaEventRecord(s.reduced, s.stream));
         prev = s.reduced;
@@ -622,7 +731,9 @@ int ctmr_table_stats(ctmr_ctx* c, uint64_t* used, uint64_t* capacity) {
     if (!c) return CTMR_E_INVALID;
     CU(c, cudaSetDevice(c->device));
     unsigned long long u = 0;
-    CU(c, cudaMemcpyAsync(&u, c->st.slots_used, sizeof u, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemsetAsync(c->small_dev + 81, 0, sizeof(unsigned long long), c->stream));
+    CU(c, launch_table_count(c->st, c->small_dev + 81, c->stream));
+    CU(c, cudaMemcpyAsync(&u, c->small_dev + 81, sizeof u, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     if (used) *used = u;
     if (capacity) *capacity = c->st.table_mask + 1;

@@ -63,6 +63,66 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
 
 // ------------------------------------------------------------------------------------------------
+// known-certificate table
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+__device__ __forceinline__ uint64_t key_hash(const uint32_t (&b)[12]) {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) h = mix64(h ^ (((uint64_t)b[i + 1] << 32) | b[i])) + 0x632BE59BD9B4E019ull * (i + 1);
+    return h;
+}
+
+// Find-or-insert of a 48-byte key body; lowest global index wins through atomicMax on ~index.
+// Returns the slot, or 0xFFFFFFFF when the table is full (error flag set).  Shared by K_insert
+// and by K_map when the insert is fused into the map kernel (single-GPU path).
+__device__ __forceinline__ uint32_t known_insert(KnownSlot* __restrict__ table, uint64_t table_mask, int* error_flag,
+                                                 const uint32_t (&body)[12], unsigned long long inv_idx) {
+    const uint64_t h = key_hash(body);
+    const unsigned long long tag_ready = (h & ~3ull) | 2ull, tag_pending = (h & ~3ull) | 1ull;
+    uint64_t pos = (h >> 7) & table_mask;
+    uint32_t probes = 0;
+    for (;;) {
+        KnownSlot* sl = table + pos;
+        unsigned long long t = ld_volatile_u64(&sl->tag);
+        if (t == 0ull) {
+            t = atomicCAS(&sl->tag, 0ull, tag_pending);
+            if (t == 0ull) {  // claimed: publish the key bytes, then flip to ready
+                uint4* bp = reinterpret_cast<uint4*>(sl->body);
+                bp[0] = make_uint4(body[0], body[1], body[2], body[3]);
+                bp[1] = make_uint4(body[4], body[5], body[6], body[7]);
+                bp[2] = make_uint4(body[8], body[9], body[10], body[11]);
+                __threadfence();
+                atomicExch(&sl->tag, tag_ready);
+                atomicMax(&sl->inv_first, inv_idx);
+                return (uint32_t)pos;
+            }
+        }
+        if ((t & ~3ull) == (h & ~3ull)) {
+            if ((t & 3ull) == 1ull) continue;  // another thread is publishing this slot: look again
+            __threadfence();
+            const uint4* bp = reinterpret_cast<const uint4*>(sl->body);
+            const uint4 b0 = bp[0], b1 = bp[1], b2 = bp[2];
+            const bool same = b0.x == body[0] && b0.y == body[1] && b0.z == body[2] && b0.w == body[3] && b1.x == body[4] &&
+                              b1.y == body[5] && b1.z == body[6] && b1.w == body[7] && b2.x == body[8] && b2.y == body[9] &&
+                              b2.z == body[10] && b2.w == body[11];
+            if (same) {
+                atomicMax(&sl->inv_first, inv_idx);
+                return (uint32_t)pos;
+            }
+        }
+        pos = (pos + 1) & table_mask;
+        if (++probes > 4096u) {  // table effectively full
+            atomicExch(error_flag, CTMR_E_TABLE_FULL);
+            return 0xFFFFFFFFu;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K_map
 // ------------------------------------------------------------------------------------------------
 template <int WARPS, int CHUNK>
@@ -305,7 +365,8 @@ struct StreamCfg {
     static constexpr int kWarpBytes = 2 * 32 * kSlot;
     static constexpr int kBlocksPerChunk = CHUNK / 64;
     static constexpr int kPieces = kSlot / 16;
-    static constexpr size_t kSmem = (size_t)WARPS * kWarpBytes + (LOADER == 1 ? (size_t)WARPS * 2 * sizeof(uint64_t) : 0);
+    // +16: the walker's word-wise header read may touch the word after the last staged byte
+    static constexpr size_t kSmem = (size_t)WARPS * kWarpBytes + 16 + (LOADER == 1 ? (size_t)WARPS * 2 * sizeof(uint64_t) : 0);
 };
 
 struct GlobalBytes {
@@ -323,7 +384,7 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
     const uint32_t slot0 = smem_u32(my_slots), slot1 = slot0 + 32 * Cfg::kSlot;
     uint32_t bar0 = 0, bar1 = 0, parity = 0;
     if (LOADER == 1) {
-        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * Cfg::kWarpBytes) + warp * 2;
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * Cfg::kWarpBytes + 16) + warp * 2;
         bar0 = smem_u32(&bars[0]);
         bar1 = smem_u32(&bars[1]);
         if (lane == 0) {
@@ -402,6 +463,7 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
         st.init();
         const uint32_t sel = 0x0123u + 0x1111u * (m & 3u);
         const uint32_t one = p.one;
+        const RotMul rm = *reinterpret_cast<const RotMul*>(p.rot_mul);
 
         for (uint32_t c = 0; c < iters; ++c) {
             const uint32_t s = c & 1u;
@@ -438,7 +500,8 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
                             wd[15] = L << 3;
                         }
                     }
-                    if (ROLLED) sha256_compress_rolled(st, wd, one);
+                    if (ROLLED >= 2) sha256_compress_wide<ROLLED - 1>(st, wd, one, rm);
+                    else if (ROLLED == 1) sha256_compress_rolled(st, wd, one);
                     else sha256_compress(st, wd, one);
                 }
             }
@@ -488,6 +551,19 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
                 uint4* kr = reinterpret_cast<uint4*>(p.keys + e);
                 kr[0] = make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)(int32_t)exp_hour, valid ? issuer : 0u);
                 *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(kr) + 14) = make_uint2(valid ? 1u : 0u, 0u);
+                if (p.slot_of) {
+                    // fused K_insert (single-GPU path): the probe's random HBM accesses hide under the
+                    // INT-bound SHA work of the other warps instead of costing a latency-bound pass
+                    uint32_t slot = 0xFFFFFFFFu;
+                    if (valid) {
+                        const uint4 k1 = kr[1], k2 = kr[2];  // the serial words the walker stored (L2-resident)
+                        const uint2 k3 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(kr) + 12);
+                        const uint32_t body[12] = {(uint32_t)(int32_t)exp_hour, issuer, k1.x, k1.y, k1.z, k1.w,
+                                                   k2.x, k2.y, k2.z, k2.w, k3.x, k3.y};
+                        slot = known_insert(p.table, p.table_mask, p.error_flag, body, ~gi);
+                    }
+                    p.slot_of[e] = slot;
+                }
             }
             if (want_sha) {
                 uint4* o = reinterpret_cast<uint4*>(p.sha256 + e * 32);
@@ -846,17 +922,6 @@ cudaError_t launch_len_order(const uint64_t* offsets, uint64_t n, uint64_t blob_
 // ------------------------------------------------------------------------------------------------
 // K_insert / K_resolve / K_pairs
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
-    return *reinterpret_cast<const volatile unsigned long long*>(p);
-}
-
-__device__ __forceinline__ uint64_t key_hash(const uint32_t (&b)[12]) {
-    uint64_t h = 0x9E3779B97F4A7C15ull;
-#pragma unroll
-    for (int i = 0; i < 12; i += 2) h = mix64(h ^ (((uint64_t)b[i + 1] << 32) | b[i])) + 0x632BE59BD9B4E019ull * (i + 1);
-    return h;
-}
-
 __global__ void __launch_bounds__(256) insert_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
                                                      uint32_t* __restrict__ slot_of) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -869,48 +934,7 @@ __global__ void __launch_bounds__(256) insert_kernel(DeviceState st, const ctmr_
     }
     const unsigned long long inv_idx = ~(((unsigned long long)q0.y << 32) | q0.x);
     const uint32_t body[12] = {q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y};
-    const uint64_t h = key_hash(body);
-    const unsigned long long tag_ready = (h & ~3ull) | 2ull, tag_pending = (h & ~3ull) | 1ull;
-    uint64_t pos = (h >> 7) & st.table_mask;
-    uint32_t probes = 0;
-    for (;;) {
-        KnownSlot* sl = st.table + pos;
-        unsigned long long t = ld_volatile_u64(&sl->tag);
-        if (t == 0ull) {
-            t = atomicCAS(&sl->tag, 0ull, tag_pending);
-            if (t == 0ull) {  // claimed: publish the key bytes, then flip to ready
-                uint4* bp = reinterpret_cast<uint4*>(sl->body);
-                bp[0] = make_uint4(body[0], body[1], body[2], body[3]);
-                bp[1] = make_uint4(body[4], body[5], body[6], body[7]);
-                bp[2] = make_uint4(body[8], body[9], body[10], body[11]);
-                __threadfence();
-                atomicExch(&sl->tag, tag_ready);
-                atomicMax(&sl->inv_first, inv_idx);
-                atomicAdd(st.slots_used, 1ull);
-                break;
-            }
-        }
-        if ((t & ~3ull) == (h & ~3ull)) {
-            if ((t & 3ull) == 1ull) continue;  // another thread is publishing this slot: look again
-            __threadfence();
-            const uint4* bp = reinterpret_cast<const uint4*>(sl->body);
-            const uint4 b0 = bp[0], b1 = bp[1], b2 = bp[2];
-            const bool same = b0.x == body[0] && b0.y == body[1] && b0.z == body[2] && b0.w == body[3] && b1.x == body[4] &&
-                              b1.y == body[5] && b1.z == body[6] && b1.w == body[7] && b2.x == body[8] && b2.y == body[9] &&
-                              b2.z == body[10] && b2.w == body[11];
-            if (same) {
-                atomicMax(&sl->inv_first, inv_idx);
-                break;
-            }
-        }
-        pos = (pos + 1) & st.table_mask;
-        if (++probes > 4096u) {  // table effectively full
-            atomicExch(st.error_flag, CTMR_E_TABLE_FULL);
-            pos = 0xFFFFFFFFull;
-            break;
-        }
-    }
-    slot_of[j] = (uint32_t)pos;
+    slot_of[j] = known_insert(st.table, st.table_mask, st.error_flag, body, inv_idx);
 }
 
 __global__ void __launch_bounds__(256) resolve_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
@@ -1037,6 +1061,19 @@ __global__ void __launch_bounds__(256) cardinality_kernel(DeviceState st, int32_
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
 }
 
+__global__ void __launch_bounds__(256) table_count_kernel(DeviceState st, unsigned long long* out) {
+    unsigned int local = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= st.table_mask; i += (uint64_t)gridDim.x * blockDim.x)
+        local += (st.table[i].tag & 3ull) == 2ull;
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+
+cudaError_t launch_table_count(const DeviceState& st, unsigned long long* out, cudaStream_t s) {
+    table_count_kernel<<<148 * 8, 256, 0, s>>>(st, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cardinality(const DeviceState& st, int32_t hour, uint32_t issuer, unsigned long long* out,
                                cudaStream_t s) {
     cardinality_kernel<<<148 * 8, 256, 0, s>>>(st, hour, issuer, out);
@@ -1145,6 +1182,11 @@ cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {
         return launch_stream_t<4, 256, 1>(p, sm_count, cps ? cps : 2, s);
     }
     static const int rolled = env_int("CTMR_MAP_ROLLED", 1);
+    if (rolled >= 2 && chunk == 128) {
+        if (rolled == 2) return launch_stream_t<8, 128, 0, 2>(p, sm_count, cps ? cps : 2, s);
+        if (rolled == 3) return launch_stream_t<8, 128, 0, 3>(p, sm_count, cps ? cps : 2, s);
+        return launch_stream_t<8, 128, 0, 4>(p, sm_count, cps ? cps : 2, s);
+    }
     if (rolled) {
         if (chunk == 128) return launch_stream_t<8, 128, 0, 1>(p, sm_count, cps ? cps : 2, s);
         if (warps == 4) return launch_stream_t<4, 256, 0, 1>(p, sm_count, cps ? cps : 2, s);

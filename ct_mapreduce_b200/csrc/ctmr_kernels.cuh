@@ -56,6 +56,7 @@ struct MapParams {
     int64_t now_sec;
     uint32_t now_frac_nonzero;
     uint32_t one;  // always 1: a multiplier ptxas cannot fold (see fadd in ctmr_device.cuh)
+    uint32_t rot_mul[12];  // 2^(32-n) multipliers of the IMAD.WIDE rotations (RotMul in ctmr_device.cuh)
     uint8_t* status;
     uint8_t* sha256;
     int64_t* exp_hour;
@@ -65,6 +66,11 @@ struct MapParams {
     unsigned long long* status_counts;
     unsigned long long* work_counter;  // [1] scratch of the dynamically scheduled map kernel
     const uint32_t* order;             // [n] length-bucketed processing order (NULL = entry order)
+    // fused K_insert (slot_of != NULL): the known-certificate table and where each entry's slot goes
+    KnownSlot* table;
+    uint64_t table_mask;
+    int* error_flag;
+    uint32_t* slot_of;
     FilterCfg filter;
 };
 
@@ -78,6 +84,7 @@ cudaError_t launch_resolve_pairs(const DeviceState& st, const ctmr_key* keys, ui
                                  const uint8_t* was_unknown, uint8_t* first_issuer_hour, cudaStream_t s);
 cudaError_t launch_issuer_prepare(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint8_t* digests,
                                   uint8_t* ok, cudaStream_t s);
+cudaError_t launch_table_count(const DeviceState& st, unsigned long long* out, cudaStream_t s);
 cudaError_t launch_cardinality(const DeviceState& st, int32_t exp_hour, uint32_t issuer, unsigned long long* out,
                                cudaStream_t s);
 cudaError_t launch_partition(const ctmr_key* keys, uint64_t n, uint32_t world, ctmr_key* keys_by_owner,

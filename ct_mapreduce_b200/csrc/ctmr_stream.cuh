@@ -63,29 +63,42 @@ struct SmemWindow {
 // sites and the map kernel's instruction footprint is what the SHA loop competes with for I-cache.
 __device__ __noinline__ uint64_t w_hdr_packed(SmemWindow rd, uint32_t pos, uint32_t lim) {
     constexpr uint64_t kFail = ~0ull;
-    Tlv t;
     if (pos + 2u > lim) return kFail;
-    const uint32_t tag = rd(pos), l = rd(pos + 1);
+    // the four bytes at `pos` in one go: two aligned 32-bit shared loads + a funnel shift
+    // (tag | len0 << 8 | len1 << 16 | len2 << 24); the window has slack past the staged bytes
+    const uint32_t a = rd.base + pos, wa = a & ~3u;
+    uint32_t lo, hi;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(wa));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(wa + 4u));
+    const uint32_t v = __funnelshift_r(lo, hi, (a & 3u) * 8u);
+    const uint32_t tag = v & 0xffu, l = (v >> 8) & 0xffu;
     if ((tag & 0x1fu) == 0x1fu) return kFail;
-    t.tag = tag;
+    uint32_t hdr, len;
     if (l < 0x80u) {
-        t.hdr = 2;
-        t.len = l;
+        hdr = 2;
+        len = l;
     } else {
         const uint32_t nb = l & 0x7fu;
         if (nb == 0u || nb > 4u || pos + 2u + nb > lim) return kFail;
-        uint32_t v = 0;
-        for (uint32_t i = 0; i < nb; ++i) {
-            if (v >= (1u << 23)) return kFail;
-            v = (v << 8) | rd(pos + 2u + i);
-            if (v == 0u) return kFail;
+        if (nb == 1u) {
+            len = (v >> 16) & 0xffu;
+            if (len < 0x80u) return kFail;  // non-minimal (covers the leading-zero rule too)
+        } else if (nb == 2u) {
+            len = ((v >> 8) & 0xff00u) | (v >> 24);
+            if (len < 0x100u) return kFail;  // superfluous leading zero
+        } else {  // 3 or 4 length octets: certificates of 64 KiB and more, byte by byte
+            len = 0;
+            for (uint32_t i = 0; i < nb; ++i) {
+                if (len >= (1u << 23)) return kFail;
+                len = (len << 8) | rd(pos + 2u + i);
+                if (len == 0u) return kFail;
+            }
+            if (len < 0x80u) return kFail;
         }
-        if (v < 0x80u) return kFail;
-        t.hdr = 2u + nb;
-        t.len = v;
+        hdr = 2u + nb;
     }
-    if (t.len > lim - pos - t.hdr) return kFail;
-    return ((uint64_t)t.len << 32) | (t.hdr << 8) | t.tag;  // registers only: no out-parameter, no stack
+    if (len > lim - pos - hdr) return kFail;
+    return ((uint64_t)len << 32) | (hdr << 8) | tag;  // registers only: no out-parameter, no stack
 }
 
 __device__ __forceinline__ bool w_hdr(SmemWindow rd, uint32_t pos, uint32_t lim, Tlv& t) {

@@ -168,6 +168,12 @@ class GpuCertDatabase:
     def read_histogram_device(self, counts_dst, n_slots: int, status_dst=None, stream=None):
         self._check(self._lib.ctmr_read_histogram_device(self._h, capi.ptr(counts_dst), n_slots, capi.ptr(status_dst), stream))
 
+    def profile_last(self):
+        """(map_ms, total_ms) of the last process_device call, from the library's own CUDA events."""
+        m, t = C.c_float(0), C.c_float(0)
+        self._check(self._lib.ctmr_profile_last(self._h, C.byref(m), C.byref(t)))
+        return m.value, t.value
+
     def reset_device(self, stream=None):
         self._check(self._lib.ctmr_reset_device(self._h, stream))
 

@@ -187,6 +187,10 @@ int ctmr_reduce_device(ctmr_ctx* ctx, const ctmr_key* keys, uint64_t m, uint8_t*
 /* map + reduce on one GPU */
 int ctmr_process_device(ctmr_ctx* ctx, const ctmr_dev_batch* batch, const ctmr_dev_out* out, void* stream);
 
+/* CUDA-event timings of the last ctmr_process_device call, valid once its stream has been synchronised:
+ * map_ms = summed duration of the K_map stage (measured on the stream it ran on), total_ms = whole call */
+int ctmr_profile_last(ctmr_ctx* ctx, float* map_ms, float* total_ms);
+
 /* multi-GPU key routing: owner(key) = hash(exp_hour, issuer) mod world, i.e. one
  * Redis set lives on one GPU.  Counting-sort the valid keys by owner. */
 int ctmr_partition_keys_device(ctmr_ctx* ctx, const ctmr_key* keys, uint64_t n, uint32_t world,

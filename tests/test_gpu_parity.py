@@ -244,3 +244,41 @@ def test_device_generator_matches_host_generator(eng, ora):
         iblob_o, ioffs_o = ora.synth_issuers(cfg_o)
         iblob_g, ioffs_g = eng.synth_issuers(cfg_g)
         assert np.array_equal(iblob_o, iblob_g) and np.array_equal(ioffs_o, ioffs_g)
+
+
+def test_process_device_pipelined_sub_batches(eng, ora):
+    """ctmr_process_device on a device-resident batch big enough to take the internal map/reduce
+    pipeline (2 sub-batches, two streams); every output against the oracle."""
+    import torch
+    from ct_mapreduce_b200 import capi
+    n = 300_000
+    kw = dict(len_mode=1, len_lo=512, len_hi=4096, dup_mode=1)
+    cfg_o, cfg_g = ora.synth_cfg(n, **kw), capi.synth_cfg(n, **kw)
+    blob, offs, idx = ora.synth_corpus(cfg_o, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg_o)
+    want = ora.DB(README_FILTER, False).process(blob, offs, iblob, ioffs, idx, NOW_NS, nthreads=8)
+    dev = torch.device("cuda:0")
+    dblob, doffs, didx, total = eng.synth_corpus_device(cfg_g, 0, n, dev)
+    with eng.GpuCertDatabase(table_capacity=1 << 20, issuer_cn_filter=README_FILTER, max_issuers=1024) as db:
+        dense = db.register_issuers(iblob, ioffs)
+        assert (dense == np.arange(cfg_g.n_issuers)).all()
+        t = {k: torch.empty((n,) + sh, dtype=dt, device=dev) for k, sh, dt in (
+            ("status", (), torch.uint8), ("sha", (32,), torch.uint8), ("exp_hour", (), torch.int64),
+            ("soff", (), torch.int32), ("slen", (), torch.int32), ("wu", (), torch.uint8), ("fi", (), torch.uint8))}
+        b = capi.DevBatch()
+        b.blob, b.blob_bytes, b.offsets, b.n = dblob.data_ptr(), total, doffs.data_ptr(), n
+        b.issuer_idx, b.issuer_map, b.issuer_map_len = didx.data_ptr(), None, 0
+        b.first_index, b.now_unix_ns = 0, NOW_NS
+        o = capi.DevOut(t["status"].data_ptr(), t["sha"].data_ptr(), t["exp_hour"].data_ptr(), t["soff"].data_ptr(),
+                        t["slen"].data_ptr(), t["wu"].data_ptr(), t["fi"].data_ptr(), None)
+        db.process_device(b, o)
+        db.check_device()
+        torch.cuda.synchronize()
+        map_ms, total_ms = db.profile_last()
+        assert 0 < map_ms <= total_ms * 1.01
+        counts = db.issuer_counts()
+    got = eng.BatchResult(t["status"].cpu().numpy(), t["sha"].cpu().numpy(), t["exp_hour"].cpu().numpy(),
+                          t["soff"].cpu().numpy().astype(np.uint32), t["slen"].cpu().numpy().astype(np.uint32),
+                          t["wu"].cpu().numpy(), t["fi"].cpu().numpy())
+    assert_same(got, want)
+    assert sum(counts.values()) == int(want.was_unknown.sum())

@@ -8,6 +8,8 @@ while read -r v; do
   [ -z "$v" ] && continue
   echo "== $W $v"; env $v $B 2>&1 | python -c "$P" || env $v $B 2>&1 | tail -5
 done <<'LIST'
-CTMR_BUCKET_BY_LENGTH=0
-CTMR_BUCKET_BY_LENGTH=1
+CTMR_MAP_ROLLED=1
+CTMR_MAP_ROLLED=2
+CTMR_MAP_ROLLED=3
+CTMR_MAP_ROLLED=4
 LIST
