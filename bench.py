@@ -109,6 +109,18 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic(entries_per_launch):
+    """dram__bytes_read+write of K_map from the committed ncu --set full capture (profiles/), scaled from the
+    captured launch size to this run's entries per launch; None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r1_map_traffic.json")
+    try:
+        t = json.load(open(p))
+        per_entry = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["entries"]
+        return per_entry * entries_per_launch, t["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -337,6 +349,8 @@ def main():
     achieved = alg_bytes / (map_ms / 1e3) / 1e9
     # N=1: 4 sub-batches x (len_order(3) + map(with insert) + resolve + pairs); N>1: + insert, partition(3), scatter
     launches_per_step = 4 * 6 if world == 1 else NSUB * (4 + 3 + 4)
+    map_launches = 4 if world == 1 else NSUB
+    traffic, traffic_src = measured_traffic(n / map_launches)
 
     # ---- e2e through the host-buffer C ABI (pinned host memory -> results on the host)
     e2e = None
@@ -402,9 +416,10 @@ def main():
                                       if world > 1 else "single GPU"},
             "sha256_gbs": total_bytes * world * K / (elapsed_ms / 1e3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": "map_stream_kernel (+ its 3 length-bucketing helper launches)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel_ms": map_ms, "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "launches_per_step": 4 if world == 1 else NSUB,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel_ms_per_step": map_ms, "kernel_ms": map_ms / map_launches,
+                         "algorithmic_bytes_per_step": int(alg_bytes), "algorithmic_bytes_per_launch": int(alg_bytes / map_launches),
+                         "launches_per_step": map_launches,
                          "note": "SHA-256 is INT-pipe bound (DESIGN.md): see profiles/ for ALU-pipe utilisation; timed while the "
                                  "reduce kernels of the previous sub-batch share the GPU"},
             "gpu_launches": launches_per_step * K,

@@ -360,7 +360,7 @@ __device__ __forceinline__ void cp_async_wait() {
 
 template <int WARPS, int CHUNK, int LOADER, int ROLLED = 0>
 struct StreamCfg {
-    static constexpr int kOverlap = 64;
+    static constexpr int kOverlap = 48;  // >= kWalkNeed, multiple of 16
     static constexpr int kSlot = kOverlap + CHUNK + 16;
     static constexpr int kWarpBytes = 2 * 32 * kSlot;
     static constexpr int kBlocksPerChunk = CHUNK / 64;
@@ -1187,6 +1187,8 @@ cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {
         if (rolled == 3) return launch_stream_t<8, 128, 0, 3>(p, sm_count, cps ? cps : 2, s);
         return launch_stream_t<8, 128, 0, 4>(p, sm_count, cps ? cps : 2, s);
     }
+    if (rolled && chunk == 64) return launch_stream_t<8, 64, 0, 1>(p, sm_count, cps ? cps : 3, s);
+    if (rolled && chunk == 128 && warps == 6) return launch_stream_t<6, 128, 0, 1>(p, sm_count, cps ? cps : 3, s);
     if (rolled) {
         if (chunk == 128) return launch_stream_t<8, 128, 0, 1>(p, sm_count, cps ? cps : 2, s);
         if (warps == 4) return launch_stream_t<4, 256, 0, 1>(p, sm_count, cps ? cps : 2, s);
