@@ -84,7 +84,7 @@ def test_store_batch_drives_remote_cache_like_the_reference(host_bin, ora, tmp_p
         elif f[0] == "PEMKEY":
             got_pemkeys.add(f[1])
         elif f[0] == "PEM":
-            got_pems[f[1]] = f[2]
+            got_pems[f[1]] = line.rstrip("\n").split(" ", 2)[2]
     assert got_sets == exp_sets
     assert got_expire == exp_expire
     assert got_dirty == exp_dirty
