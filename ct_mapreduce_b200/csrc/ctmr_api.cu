@@ -420,7 +420,7 @@ int ctmr_map_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o,
     MapParams p;
     fill_map_params(c, b, o, p);
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
-    if (c->bucket_by_length && b->n > 64) {
+    if (c->bucket_by_length && b->n > 64 && p.sha256) {  // the light (no-fingerprint) kernel has no lock-step loop to balance
         if (b->n > c->order_cap) {
             CU(c, cudaDeviceSynchronize());
             cudaFree(c->order_scratch);
@@ -501,7 +501,7 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
         MapParams p;
         fill_map_params(c, &sb, &so, p, 3, c->fuse_insert ? c->slot_scratch + lo : nullptr);
         CU(c, cudaEventRecord(c->ev_map0[k], c->stream_a));
-        if (c->bucket_by_length && cnt > 64) {
+        if (c->bucket_by_length && cnt > 64 && p.sha256) {
             CU(c, launch_len_order(sb.offsets, cnt, sb.blob_bytes, c->len_hist_sub[k], c->order_scratch + lo, c->stream_a));
             p.order = c->order_scratch + lo;
         }
@@ -657,7 +657,7 @@ int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets
         dout.keys = s.keys;
         MapParams p;
         fill_map_params(c, &db, &dout, p, sub % kStages, c->fuse_insert ? s.slot_of : nullptr);
-        if (c->bucket_by_length && cnt > 64) {
+        if (c->bucket_by_length && cnt > 64 && p.sha256) {
             CU(c, launch_len_order(s.offsets, cnt, db.blob_bytes, s.len_hist, s.order, s.stream));
             p.order = s.order;
         }

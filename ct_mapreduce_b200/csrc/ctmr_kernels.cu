@@ -342,6 +342,103 @@ cudaError_t launch_map_v1(const MapParams& p, int sm_count, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K_map_light: the map WITHOUT the whole-certificate fingerprint (CTMR_F_NO_FINGERPRINT, i.e. the
+// reference's own semantics: it never hashes the leaf).  With no SHA-256 there is
+// nothing to stream: the walker touches ~1/3 of a certificate's 32-byte sectors (TBS header,
+// names, validity, the extension headers, the trailing signature header) and skips the key,
+// the padding and the signature.  So: no shared memory, one thread per certificate, byte loads
+// through L1 (the full 256 KB is available as cache), 32 resident warps per SM to hide the pointer
+// chase.  The streaming kernel, which must stage every byte, tops out at ~2.0 TB/s here.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4) map_light_kernel(const __grid_constant__ MapParams p) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = e < p.n;
+    uint32_t status = CTMR_ST_PARSE_ERR;
+    if (act) {
+        const uint64_t off = p.offsets[e], end = p.offsets[e + 1];
+        const bool bad_span = end < off || end > p.blob_bytes || end - off > 0x7fffffffull;
+        const uint32_t L = bad_span ? 0u : (uint32_t)(end - off);
+        const uint8_t* d = p.blob + off;
+        ParsedCert pc;
+        uint32_t issuer = CTMR_ISSUER_NONE;
+        int64_t exp_hour = 0;
+        if (!bad_span && parse_cert(d, L, pc)) {
+            status = CTMR_ST_OK;
+            exp_hour = pc.not_after >= 0 ? pc.not_after / 3600 : -((-pc.not_after + 3599) / 3600);
+            if ((pc.flags & (PC_BC_VALID | PC_IS_CA)) == (PC_BC_VALID | PC_IS_CA)) {
+                status = CTMR_ST_FILTER_CA;
+            } else if (!p.filter.log_expired &&
+                       (pc.not_after < p.now_sec || (pc.not_after == p.now_sec && p.now_frac_nonzero))) {
+                status = CTMR_ST_FILTER_EXPIRED;
+            } else if (p.filter.filter_nonempty) {
+                bool skip = true;
+                const uint32_t cnl = (pc.flags & PC_HAS_CN) ? pc.cn_len : 0u;
+                for (uint32_t q = 0; q < p.filter.n_prefix && skip; ++q) {
+                    const uint32_t po = p.filter.off[q], pl = p.filter.off[q + 1] - po;
+                    if (pl > cnl) continue;
+                    bool eq = true;
+                    for (uint32_t i = 0; i < pl; ++i)
+                        if (__ldg(d + pc.cn_off + i) != p.filter.bytes[po + i]) { eq = false; break; }
+                    if (eq) skip = false;
+                }
+                if (skip) status = CTMR_ST_FILTER_CN;
+            }
+            if (status == CTMR_ST_OK) {
+                uint32_t k = p.issuer_idx ? p.issuer_idx[e] : CTMR_ISSUER_NONE;
+                if (k != CTMR_ISSUER_NONE && p.issuer_map) k = k < p.issuer_map_len ? p.issuer_map[k] : CTMR_ISSUER_NONE;
+                issuer = k;
+                if (k == CTMR_ISSUER_NONE) status = CTMR_ST_NO_ISSUER;
+                else if (k == CTMR_ISSUER_BAD) status = CTMR_ST_ISSUER_PARSE_ERR;
+                else if (pc.serial_len > CTMR_MAX_SERIAL) status = CTMR_ST_SERIAL_TOO_LONG;
+            }
+        } else {
+            pc.serial_off = pc.serial_len = 0;
+        }
+        if (p.status) p.status[e] = (uint8_t)status;
+        if (p.exp_hour) p.exp_hour[e] = exp_hour;
+        if (p.serial_off) p.serial_off[e] = pc.serial_off;
+        if (p.serial_len) p.serial_len[e] = pc.serial_len;
+        if (p.keys) {
+            const bool valid = status == CTMR_ST_OK;
+            uint32_t body[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) body[i] = 0;
+            if (valid) {
+                body[0] = (uint32_t)(int32_t)exp_hour;
+                body[1] = issuer;
+                body[2] = pc.serial_len;
+#pragma unroll 1
+                for (uint32_t i = 0; i < pc.serial_len; ++i) {  // {len, serial[39]} packed little-endian from byte 8
+                    const uint32_t at = i + 1u;
+                    const uint32_t b = __ldg(d + pc.serial_off + i) << (8u * (at & 3u));
+                    switch (at >> 2) {  // static register indices
+                    case 0: body[2] |= b; break; case 1: body[3] |= b; break; case 2: body[4] |= b; break;
+                    case 3: body[5] |= b; break; case 4: body[6] |= b; break; case 5: body[7] |= b; break;
+                    case 6: body[8] |= b; break; case 7: body[9] |= b; break; case 8: body[10] |= b; break;
+                    default: body[11] |= b; break;
+                    }
+                }
+            }
+            const uint64_t gi = p.first_index + e;
+            uint4* kr = reinterpret_cast<uint4*>(p.keys + e);
+            kr[0] = make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), body[0], body[1]);
+            kr[1] = make_uint4(body[2], body[3], body[4], body[5]);
+            kr[2] = make_uint4(body[6], body[7], body[8], body[9]);
+            kr[3] = make_uint4(body[10], body[11], valid ? 1u : 0u, 0u);
+            if (p.slot_of) p.slot_of[e] = valid ? known_insert(p.table, p.table_mask, p.error_flag, body, ~gi) : 0xFFFFFFFFu;
+        }
+    }
+    if (p.status_counts) {
+        const uint32_t amask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const uint32_t peers = __match_any_sync(amask, status);
+            if ((threadIdx.x & 31u) == (uint32_t)__ffs(peers) - 1u)
+                atomicAdd(p.status_counts + status, (unsigned long long)__popc(peers));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K_map v2: single-pass streaming map.  The DER walker (ctmr_stream.cuh) and the SHA-256 loop both
 // eat from the same per-lane shared-memory window; global memory is touched once per byte, by
 // asynchronous copies only.  Chunks overlap by kOverlap bytes so that a TLV header (and the small
@@ -1166,6 +1263,11 @@ cudaError_t launch_scatter_bits(const uint8_t* a, const uint8_t* b, const uint32
 // environment overrides exist for the A/B runs recorded under profiles/.
 cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {
     if (p.n == 0) return cudaSuccess;
+    static const int light = env_int("CTMR_MAP_LIGHT", 1);
+    if (p.sha256 == nullptr && light) {  // no fingerprint requested: nothing to stream
+        map_light_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, s>>>(p);
+        return cudaGetLastError();
+    }
     static const int variant = env_int("CTMR_MAP_VARIANT", 2);   // 1: v1 (global-memory walk), 2: streaming walk
     static const int loader = env_int("CTMR_MAP_LOADER", 0);     // 0: cp.async (LDGSTS), 1: TMA bulk copy
     static const int warps = env_int("CTMR_MAP_WARPS", 8);
