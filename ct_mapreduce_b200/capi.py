@@ -27,7 +27,8 @@ EXPORTS = [
     "ctmr_register_issuers", "ctmr_issuer_digest", "ctmr_issuer_count", "ctmr_process_batch", "ctmr_issuer_counts",
     "ctmr_set_cardinality", "ctmr_status_counters", "ctmr_table_stats", "ctmr_map_device", "ctmr_reduce_device",
     "ctmr_process_device", "ctmr_partition_keys_device", "ctmr_scatter_bits_device", "ctmr_read_histogram_device",
-    "ctmr_check_device", "ctmr_reset_device", "ctmr_profile_last", "ctmr_synth_offsets_device", "ctmr_synth_write_device", "ctmr_synth_truth_device", "ctmr_synth_issuers_host",
+    "ctmr_check_device", "ctmr_reset_device", "ctmr_profile_last", "ctmr_preload_known", "ctmr_snapshot_size",
+    "ctmr_snapshot_save", "ctmr_snapshot_load", "ctmr_synth_offsets_device", "ctmr_synth_write_device", "ctmr_synth_truth_device", "ctmr_synth_issuers_host",
 ]
 
 
@@ -118,6 +119,10 @@ def load():
     L.ctmr_read_histogram_device.argtypes = [vp, vp, u32, vp, vp]
     L.ctmr_check_device.argtypes = [vp, vp]
     L.ctmr_reset_device.argtypes = [vp, vp]
+    L.ctmr_preload_known.argtypes = [vp, i64, vp, vp, vp, u64]
+    L.ctmr_snapshot_size.argtypes = [vp, C.POINTER(u64)]
+    L.ctmr_snapshot_save.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.ctmr_snapshot_load.argtypes = [vp, vp, u64]
     L.ctmr_profile_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.ctmr_synth_offsets_device.argtypes = [C.POINTER(SynthCfg), u64, u64, vp, C.POINTER(u64), vp]
     L.ctmr_synth_write_device.argtypes = [C.POINTER(SynthCfg), u64, u64, vp, vp, vp, vp]

@@ -686,6 +686,122 @@ int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets
     return ctmr_check_device(c, nullptr);
 }
 
+// ------------------------------------------------------------------------------------------------ warm start / checkpoint
+int ctmr_preload_known(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], const uint8_t* serial_blob,
+                       const uint64_t* serial_offsets, uint64_t n) {
+    if (!c || !digest || (n && (!serial_blob || !serial_offsets))) return fail(c, CTMR_E_INVALID, "bad argument");
+    if (exp_hour > INT32_MAX || exp_hour < INT32_MIN) return fail(c, CTMR_E_INVALID, "exp_hour out of range");
+    CU(c, cudaSetDevice(c->device));
+    // the issuer may be unknown to this ctx (state written by an earlier process): register its digest
+    std::string dk(reinterpret_cast<const char*>(digest), 32);
+    uint32_t issuer;
+    auto it = c->issuer_by_digest.find(dk);
+    if (it != c->issuer_by_digest.end()) {
+        issuer = it->second;
+    } else {
+        if (c->digests.size() >= c->st.max_issuers) return fail(c, CTMR_E_TOO_MANY_ISSUERS, "more distinct issuers than config.max_issuers");
+        issuer = (uint32_t)c->digests.size();
+        std::array<uint8_t, 32> a;
+        std::memcpy(a.data(), digest, 32);
+        c->digests.push_back(a);
+        c->issuer_by_digest.emplace(std::move(dk), issuer);
+    }
+    if (!n) return CTMR_OK;
+    // key records with index 0 .. n-1 BELOW every batch index: preloaded keys always win "first seen".
+    // Batch indices are shifted up by the number of preloaded keys (next_index).
+    std::vector<ctmr_key> keys(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t len = serial_offsets[i + 1] - serial_offsets[i];
+        if (serial_offsets[i + 1] < serial_offsets[i] || len == 0 || len > CTMR_MAX_SERIAL)
+            return fail(c, CTMR_E_INVALID, "preloaded serial empty or longer than CTMR_MAX_SERIAL");
+        std::memset(&keys[i], 0, sizeof(ctmr_key));
+        keys[i].index = c->next_index + i;
+        keys[i].exp_hour = (int32_t)exp_hour;
+        keys[i].issuer = issuer;
+        keys[i].serial_len = (uint8_t)len;
+        std::memcpy(keys[i].serial, serial_blob + serial_offsets[i], len);
+        keys[i].valid = 1;
+    }
+    int rc = ensure_scratch(c, n);
+    if (rc) return rc;
+    CU(c, cudaMemcpyAsync(c->keys_scratch, keys.data(), n * sizeof(ctmr_key), cudaMemcpyHostToDevice, c->stream));
+    rc = reduce_on(c, c->keys_scratch, n, c->slot_scratch, c->pair_scratch, c->bits_scratch, c->bits_scratch + n, c->stream);
+    if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->next_index += n;
+    return ctmr_check_device(c, nullptr);
+}
+
+namespace {
+struct SnapHeader {
+    char magic[8];  // "CTMRSNP1"
+    uint64_t table_slots, pair_slots, max_issuers, n_issuers, next_index;
+};
+}  // namespace
+
+int ctmr_snapshot_size(ctmr_ctx* c, uint64_t* bytes) {
+    if (!c || !bytes) return fail(c, CTMR_E_INVALID, "bad argument");
+    *bytes = sizeof(SnapHeader) + (c->st.table_mask + 1) * sizeof(KnownSlot) + (c->st.pair_mask + 1) * sizeof(PairSlot) +
+             c->st.max_issuers * sizeof(uint64_t) + CTMR_ST__COUNT * sizeof(uint64_t) + c->digests.size() * 32;
+    return CTMR_OK;
+}
+
+int ctmr_snapshot_save(ctmr_ctx* c, uint8_t* buf, uint64_t cap, uint64_t* written) {
+    uint64_t need = 0;
+    int rc = ctmr_snapshot_size(c, &need);
+    if (rc) return rc;
+    if (!buf || cap < need) return fail(c, CTMR_E_INVALID, "snapshot buffer too small");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    SnapHeader h{};
+    std::memcpy(h.magic, "CTMRSNP1", 8);
+    h.table_slots = c->st.table_mask + 1;
+    h.pair_slots = c->st.pair_mask + 1;
+    h.max_issuers = c->st.max_issuers;
+    h.n_issuers = c->digests.size();
+    h.next_index = c->next_index;
+    uint8_t* p = buf;
+    std::memcpy(p, &h, sizeof h); p += sizeof h;
+    CU(c, cudaMemcpy(p, c->st.table, h.table_slots * sizeof(KnownSlot), cudaMemcpyDeviceToHost)); p += h.table_slots * sizeof(KnownSlot);
+    CU(c, cudaMemcpy(p, c->st.pairs, h.pair_slots * sizeof(PairSlot), cudaMemcpyDeviceToHost)); p += h.pair_slots * sizeof(PairSlot);
+    CU(c, cudaMemcpy(p, c->st.issuer_counts, h.max_issuers * sizeof(uint64_t), cudaMemcpyDeviceToHost)); p += h.max_issuers * sizeof(uint64_t);
+    CU(c, cudaMemcpy(p, c->st.status_counts, CTMR_ST__COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost)); p += CTMR_ST__COUNT * sizeof(uint64_t);
+    for (const auto& d : c->digests) { std::memcpy(p, d.data(), 32); p += 32; }
+    if (written) *written = (uint64_t)(p - buf);
+    return CTMR_OK;
+}
+
+int ctmr_snapshot_load(ctmr_ctx* c, const uint8_t* buf, uint64_t bytes) {
+    if (!c || !buf || bytes < sizeof(SnapHeader)) return fail(c, CTMR_E_INVALID, "bad snapshot");
+    SnapHeader h;
+    std::memcpy(&h, buf, sizeof h);
+    if (std::memcmp(h.magic, "CTMRSNP1", 8) != 0) return fail(c, CTMR_E_INVALID, "not a ctmr snapshot");
+    if (h.table_slots != c->st.table_mask + 1 || h.pair_slots != c->st.pair_mask + 1 || h.max_issuers != c->st.max_issuers)
+        return fail(c, CTMR_E_INVALID, "snapshot was taken with different capacities (table / pairs / max_issuers)");
+    const uint64_t need = sizeof h + h.table_slots * sizeof(KnownSlot) + h.pair_slots * sizeof(PairSlot) +
+                          h.max_issuers * sizeof(uint64_t) + CTMR_ST__COUNT * sizeof(uint64_t) + h.n_issuers * 32;
+    if (bytes < need || h.n_issuers > h.max_issuers) return fail(c, CTMR_E_INVALID, "truncated snapshot");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    const uint8_t* p = buf + sizeof h;
+    CU(c, cudaMemcpy(c->st.table, p, h.table_slots * sizeof(KnownSlot), cudaMemcpyHostToDevice)); p += h.table_slots * sizeof(KnownSlot);
+    CU(c, cudaMemcpy(c->st.pairs, p, h.pair_slots * sizeof(PairSlot), cudaMemcpyHostToDevice)); p += h.pair_slots * sizeof(PairSlot);
+    CU(c, cudaMemcpy(c->st.issuer_counts, p, h.max_issuers * sizeof(uint64_t), cudaMemcpyHostToDevice)); p += h.max_issuers * sizeof(uint64_t);
+    CU(c, cudaMemcpy(c->st.status_counts, p, CTMR_ST__COUNT * sizeof(uint64_t), cudaMemcpyHostToDevice)); p += CTMR_ST__COUNT * sizeof(uint64_t);
+    c->digests.clear();
+    c->issuer_by_digest.clear();
+    c->issuer_by_der.clear();  // DER memo is rebuilt lazily; dense indices come from the digests
+    for (uint64_t i = 0; i < h.n_issuers; ++i) {
+        std::array<uint8_t, 32> a;
+        std::memcpy(a.data(), p, 32);
+        c->digests.push_back(a);
+        c->issuer_by_digest.emplace(std::string(reinterpret_cast<const char*>(p), 32), (uint32_t)i);
+        p += 32;
+    }
+    c->next_index = h.next_index;
+    return CTMR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ read side
 int ctmr_issuer_counts(ctmr_ctx* c, uint8_t* digests, uint64_t* counts, size_t* n) {
     if (!c || !n) return fail(c, CTMR_E_INVALID, "bad argument");

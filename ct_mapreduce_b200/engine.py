@@ -180,6 +180,28 @@ class GpuCertDatabase:
     def check_device(self, stream=None):
         self._check(self._lib.ctmr_check_device(self._h, stream))
 
+    # ------------------------------------------------------------------ warm start / checkpoint
+    def preload_known(self, exp_hour: int, issuer_digest: bytes, serials):
+        """Seed one "serials::<expDate>::<issuer>" set (e.g. KnownCertificates.Known() read back from Redis)."""
+        serials = [bytes(x) for x in serials]
+        offs = np.zeros(len(serials) + 1, np.uint64)
+        offs[1:] = np.cumsum([len(x) for x in serials], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(serials) or b"\0", np.uint8).copy()
+        d = (C.c_uint8 * 32).from_buffer_copy(issuer_digest)
+        self._check(self._lib.ctmr_preload_known(self._h, exp_hour, d, capi.ptr(blob), capi.ptr(offs), len(serials)))
+
+    def snapshot(self) -> np.ndarray:
+        need = C.c_uint64(0)
+        self._check(self._lib.ctmr_snapshot_size(self._h, C.byref(need)))
+        buf = np.empty(need.value, np.uint8)
+        wrote = C.c_uint64(0)
+        self._check(self._lib.ctmr_snapshot_save(self._h, capi.ptr(buf), buf.size, C.byref(wrote)))
+        return buf[:wrote.value]
+
+    def restore(self, snap: np.ndarray):
+        snap = np.ascontiguousarray(snap, np.uint8)
+        self._check(self._lib.ctmr_snapshot_load(self._h, capi.ptr(snap), snap.size))
+
     # ------------------------------------------------------------------ reducers' read side
     def get_known_certificates(self, exp_hour: int, issuer_digest: bytes) -> KnownCertificatesView:
         return KnownCertificatesView(self, exp_hour, issuer_digest)

@@ -139,6 +139,22 @@ int ctmr_set_cardinality(ctmr_ctx* ctx, int64_t exp_hour, const uint8_t issuer_d
 int ctmr_status_counters(ctmr_ctx* ctx, uint64_t out[CTMR_ST__COUNT]);
 int ctmr_table_stats(ctmr_ctx* ctx, uint64_t* slots_used, uint64_t* capacity);
 
+/* ---- warm start / checkpoint -------------------------------------------- */
+/* Seed the known-certificate table from pre-existing state, e.g. the members of the Redis set
+ * "serials::<expDate>::<issuer>" read back with KnownCertificates.Known() (storage/knowncertificates.go:65-96):
+ * `n` serials, serial i = serial_blob[serial_offsets[i] .. serial_offsets[i+1]).  Preloaded keys count as
+ * seen before every batch: WasUnknown answers false for them, per-issuer counts include them, and the
+ * (issuer, expDate) pair counts as already allocated.  HOST buffers. */
+int ctmr_preload_known(ctmr_ctx* ctx, int64_t exp_hour, const uint8_t issuer_digest[32], const uint8_t* serial_blob,
+                       const uint64_t* serial_offsets /* [n+1] */, uint64_t n);
+/* Snapshot of the derived device state (tables, histograms, issuer registry, next entry index) into a
+ * caller buffer, and its restoration into a ctx created with the same capacities.  ctmr_snapshot_size
+ * gives the bytes needed.  The reference's analogue is the state it keeps in Redis between runs
+ * (storage/rediscache.go); its own resume logic is cmd/ct-fetch/ct-fetch.go:288-300. */
+int ctmr_snapshot_size(ctmr_ctx* ctx, uint64_t* bytes);
+int ctmr_snapshot_save(ctmr_ctx* ctx, uint8_t* buf, uint64_t cap, uint64_t* written);
+int ctmr_snapshot_load(ctmr_ctx* ctx, const uint8_t* buf, uint64_t bytes);
+
 /* ---- device-resident entry points ---------------------------------------------------------- */
 /* Same path with every buffer already in HBM on ctx's device (benchmarks, multi-GPU orchestration,
  * hosts that receive entries by GPUDirect).  `stream` is a cudaStream_t passed as void*; NULL =

@@ -282,3 +282,57 @@ def test_process_device_pipelined_sub_batches(eng, ora):
                           t["wu"].cpu().numpy(), t["fi"].cpu().numpy())
     assert_same(got, want)
     assert sum(counts.values()) == int(want.was_unknown.sum())
+
+
+def _two_halves(ora, n=8000):
+    cfg = ora.synth_cfg(n, dup_mode=1)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    odb = ora.DB(README_FILTER, False)
+    h = n // 2
+    ra = odb.process(blob, offs[:h + 1], iblob, ioffs, idx[:h], NOW_NS)
+    rb = odb.process(blob, offs[h:], iblob, ioffs, idx[h:], NOW_NS)
+    return cfg, blob, offs, idx, iblob, ioffs, h, ra, rb, odb
+
+
+def test_warm_start_from_existing_sets(eng, ora):
+    """a fresh ctx seeded from the Redis sets an earlier run left behind answers the
+    second half of the log exactly as the uninterrupted reference would."""
+    cfg, blob, offs, idx, iblob, ioffs, h, ra, rb, odb = _two_halves(ora)
+    digests = {}
+    for k in range(cfg.n_issuers):
+        der = iblob[ioffs[k]:ioffs[k + 1]].tobytes()
+        rc, c = ora.parse_cert(der)
+        digests[k] = ora.issuer_id(der[c.spki_off:c.spki_off + c.spki_len])[0]
+    sets = {}  # what Redis holds after the first half: (hour, issuer) -> serials
+    for i in np.nonzero(ra.was_unknown)[0]:
+        a = int(offs[i]) + int(ra.serial_off[i])
+        sets.setdefault((int(ra.exp_hour[i]), digests[int(idx[i])]), []).append(blob[a:a + int(ra.serial_len[i])].tobytes())
+    with eng.GpuCertDatabase(issuer_cn_filter=README_FILTER, table_capacity=1 << 16) as db:
+        for (hour, dig), serials in sets.items():
+            db.preload_known(hour, dig, serials)
+        rg = db.store_batch(blob, offs[h:], iblob, ioffs, idx[h:], NOW_NS)
+        assert_same(rg, rb)
+        assert {k: v for k, v in db.issuer_counts().items() if v} == odb.issuer_counts()
+        (hour, dig), serials = next(iter(sets.items()))
+        assert db.get_known_certificates(hour, dig).count() == odb.set_cardinality(hour, dig)
+
+
+def test_snapshot_and_restore(eng, ora):
+    """Checkpoint the derived device state after the first half, restore it into a new ctx, continue."""
+    cfg, blob, offs, idx, iblob, ioffs, h, ra, rb, odb = _two_halves(ora)
+    kw = dict(issuer_cn_filter=README_FILTER, table_capacity=1 << 16, max_issuers=512, pair_capacity_log2=18)
+    with eng.GpuCertDatabase(**kw) as db1:
+        r1 = db1.store_batch(blob, offs[:h + 1], iblob, ioffs, idx[:h], NOW_NS)
+        assert_same(r1, ra)
+        snap = db1.snapshot().copy()
+    with eng.GpuCertDatabase(**kw) as db2:
+        db2.restore(snap)
+        r2 = db2.store_batch(blob, offs[h:], iblob, ioffs, idx[h:], NOW_NS)
+        assert_same(r2, rb)
+        assert {k: v for k, v in db2.issuer_counts().items() if v} == odb.issuer_counts()
+        assert np.array_equal(db2.status_counters(), odb.filter_counters())
+    from ct_mapreduce_b200 import capi
+    with eng.GpuCertDatabase(issuer_cn_filter=README_FILTER, table_capacity=1 << 15, max_issuers=512, pair_capacity_log2=18) as db3:
+        with pytest.raises(capi.CtmrError):
+            db3.restore(snap)  # capacities differ
