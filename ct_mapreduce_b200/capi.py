@@ -43,7 +43,8 @@ class Config(C.Structure):
 
 class Out(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("status", "sha256", "exp_hour", "serial_off", "serial_len", "was_unknown", "first_issuer_hour")]
+                ("status", "sha256", "exp_hour", "serial_off", "serial_len", "was_unknown", "first_issuer_hour",
+                 "issuer_name_off", "issuer_name_len", "crldp_off", "crldp_len", "first_issuer_dn", "first_crldp")]
 
 
 class DevBatch(C.Structure):
@@ -56,7 +57,8 @@ class DevBatch(C.Structure):
 
 class DevOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("status", "sha256", "exp_hour", "serial_off", "serial_len", "was_unknown", "first_issuer_hour", "keys")]
+                ("status", "sha256", "exp_hour", "serial_off", "serial_len", "was_unknown", "first_issuer_hour", "keys",
+                 "issuer_name_off", "issuer_name_len", "crldp_off", "crldp_len", "first_issuer_dn", "first_crldp")]
 
 
 class SynthCfg(C.Structure):

@@ -42,6 +42,9 @@ struct Stage {
     uint32_t* pair_slot = nullptr;
     uint32_t* order = nullptr;
     unsigned int* len_hist = nullptr;
+    uint32_t* spans = nullptr;       // [4][E]: issuer name off/len, crldp off/len
+    uint32_t* meta_slots = nullptr;  // [2*E]
+    uint8_t* first_meta = nullptr;   // [2][E]: first_issuer_dn, first_crldp
 };
 
 }  // namespace
@@ -68,6 +71,7 @@ struct ctmr_ctx {
     uint32_t* slot_scratch = nullptr;
     uint32_t* pair_scratch = nullptr;
     uint8_t* bits_scratch = nullptr;
+    uint32_t* meta_scratch = nullptr;  // [2*cap]
     uint64_t scratch_cap = 0;
     uint32_t* order_scratch = nullptr;  // length-bucketed order of the device entry points
     uint64_t order_cap = 0;
@@ -153,6 +157,9 @@ int ensure_stages(ctmr_ctx* c) {
         CU(c, cudaMalloc(&s.pair_slot, E * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.order, E * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.len_hist, 256 * sizeof(unsigned int)));
+        CU(c, cudaMalloc(&s.spans, 4 * E * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.meta_slots, 2 * E * sizeof(uint32_t)));
+        CU(c, cudaMalloc(&s.first_meta, 2 * E));
     }
     c->stages_ready = true;
     return CTMR_OK;
@@ -162,12 +169,14 @@ int ensure_scratch(ctmr_ctx* c, uint64_t n) {
     if (n <= c->scratch_cap) return CTMR_OK;
     CU(c, cudaDeviceSynchronize());
     cudaFree(c->keys_scratch); cudaFree(c->slot_scratch); cudaFree(c->pair_scratch); cudaFree(c->bits_scratch);
-    c->keys_scratch = nullptr; c->slot_scratch = c->pair_scratch = nullptr; c->bits_scratch = nullptr;
+    cudaFree(c->meta_scratch);
+    c->keys_scratch = nullptr; c->slot_scratch = c->pair_scratch = nullptr; c->bits_scratch = nullptr; c->meta_scratch = nullptr;
     c->scratch_cap = 0;
     CU(c, cudaMalloc(&c->keys_scratch, n * sizeof(ctmr_key)));
     CU(c, cudaMalloc(&c->slot_scratch, n * sizeof(uint32_t)));
     CU(c, cudaMalloc(&c->pair_scratch, n * sizeof(uint32_t)));
     CU(c, cudaMalloc(&c->bits_scratch, 2 * n));
+    CU(c, cudaMalloc(&c->meta_scratch, 2 * n * sizeof(uint32_t)));
     c->scratch_cap = n;
     return CTMR_OK;
 }
@@ -199,6 +208,12 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
     p.serial_off = o->serial_off;
     p.serial_len = o->serial_len;
     p.keys = o->keys;
+    if (o->issuer_name_off && o->issuer_name_len && o->crldp_off && o->crldp_len) {
+        p.issuer_name_off = o->issuer_name_off;
+        p.issuer_name_len = o->issuer_name_len;
+        p.crldp_off = o->crldp_off;
+        p.crldp_len = o->crldp_len;
+    }
     p.status_counts = c->st.status_counts;
     p.work_counter = c->small_dev + 84 + counter_slot;  // one per pipeline stage + one for the device entry points
     p.filter = c->filter;
@@ -286,6 +301,9 @@ int ctmr_create(const ctmr_config* cfg, ctmr_ctx** out) {
     c->st.pair_mask = (1ull << plog) - 1;
     CUC(cudaMalloc(&c->st.pairs, (c->st.pair_mask + 1) * sizeof(PairSlot)));
     CUC(cudaMemsetAsync(c->st.pairs, 0, (c->st.pair_mask + 1) * sizeof(PairSlot), c->stream));
+    c->st.meta_mask = (1ull << 20) - 1;  // IssuerMetadata string identities: O(issuers x few)
+    CUC(cudaMalloc(&c->st.meta, (c->st.meta_mask + 1) * sizeof(MetaSlot)));
+    CUC(cudaMemsetAsync(c->st.meta, 0, (c->st.meta_mask + 1) * sizeof(MetaSlot), c->stream));
     c->st.max_issuers = cfg->max_issuers ? cfg->max_issuers : 65536;
     CUC(cudaMalloc(&c->st.issuer_counts, c->st.max_issuers * sizeof(unsigned long long)));
     CUC(cudaMemsetAsync(c->st.issuer_counts, 0, c->st.max_issuers * sizeof(unsigned long long), c->stream));
@@ -314,13 +332,13 @@ void ctmr_destroy(ctmr_ctx* c) {
     for (Stage& s : c->stages) {
         cudaFree(s.blob); cudaFree(s.offsets); cudaFree(s.issuer_idx); cudaFree(s.status); cudaFree(s.sha);
         cudaFree(s.exp_hour); cudaFree(s.serial_off); cudaFree(s.serial_len); cudaFree(s.was_unknown); cudaFree(s.first);
-        cudaFree(s.keys); cudaFree(s.slot_of); cudaFree(s.pair_slot); cudaFree(s.order); cudaFree(s.len_hist);
+        cudaFree(s.keys); cudaFree(s.slot_of); cudaFree(s.pair_slot); cudaFree(s.order); cudaFree(s.len_hist); cudaFree(s.spans); cudaFree(s.meta_slots); cudaFree(s.first_meta);
         if (s.reduced) cudaEventDestroy(s.reduced);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     cudaFree(c->st.table); cudaFree(c->st.pairs); cudaFree(c->st.issuer_counts); cudaFree(c->small_dev);
     cudaFree(c->issuer_map_dev); cudaFree(c->keys_scratch); cudaFree(c->slot_scratch); cudaFree(c->pair_scratch);
-    cudaFree(c->bits_scratch); cudaFree(c->order_scratch); cudaFree(c->len_hist);
+    cudaFree(c->bits_scratch); cudaFree(c->meta_scratch); cudaFree(c->order_scratch); cudaFree(c->len_hist); cudaFree(c->st.meta);
     for (int k = 0; k < 8; ++k) {
         cudaFree(c->len_hist_sub[k]);
         if (c->ev_map0[k]) cudaEventDestroy(c->ev_map0[k]);
@@ -474,6 +492,9 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
             CU(c, cudaMalloc(&c->len_hist_sub[k], 256 * sizeof(unsigned int)));
         }
     }
+    const bool want_meta = o->first_issuer_dn || o->first_crldp;
+    if (want_meta && !(o->issuer_name_off && o->issuer_name_len && o->crldp_off && o->crldp_len))
+        return fail(c, CTMR_E_INVALID, "first_issuer_dn / first_crldp need the four span outputs as well");
     cudaStream_t user = stream ? (cudaStream_t)stream : c->stream;
     // The map half is INT-pipe bound and the reduce half is latency/atomic bound: run sub-batch
     // k+1's K_map (stream A) while sub-batch k's insert/resolve/pairs run (stream B).
@@ -498,6 +519,10 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
         so.serial_off = o->serial_off ? o->serial_off + lo : nullptr;
         so.serial_len = o->serial_len ? o->serial_len + lo : nullptr;
         so.keys = keys + lo;
+        so.issuer_name_off = o->issuer_name_off ? o->issuer_name_off + lo : nullptr;
+        so.issuer_name_len = o->issuer_name_len ? o->issuer_name_len + lo : nullptr;
+        so.crldp_off = o->crldp_off ? o->crldp_off + lo : nullptr;
+        so.crldp_len = o->crldp_len ? o->crldp_len + lo : nullptr;
         MapParams p;
         fill_map_params(c, &sb, &so, p, 3, c->fuse_insert ? c->slot_scratch + lo : nullptr);
         CU(c, cudaEventRecord(c->ev_map0[k], c->stream_a));
@@ -511,6 +536,10 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
         rc = reduce_on(c, keys + lo, cnt, c->slot_scratch + lo, c->pair_scratch + lo, wu + lo, fi + lo, c->stream_b,
                        c->fuse_insert);
         if (rc) return rc;
+        if (want_meta)  // IssuerMetadata string identities of this sub-batch's new certificates
+            CU(c, launch_meta(c->st, sb.blob, sb.offsets, keys + lo, cnt, wu + lo, so.issuer_name_off, so.issuer_name_len, so.crldp_off,
+                              so.crldp_len, c->meta_scratch + 2 * lo, o->first_issuer_dn ? o->first_issuer_dn + lo : nullptr,
+                              o->first_crldp ? o->first_crldp + lo : nullptr, c->stream_b));
         CU(c, cudaEventRecord(c->ev_red1[k], c->stream_b));
     }
     c->last_sub = nsub;
@@ -573,6 +602,7 @@ int ctmr_reset_device(ctmr_ctx* c, void* stream) {
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     CU(c, cudaMemsetAsync(c->st.table, 0, (c->st.table_mask + 1) * sizeof(KnownSlot), s));
     CU(c, cudaMemsetAsync(c->st.pairs, 0, (c->st.pair_mask + 1) * sizeof(PairSlot), s));
+    CU(c, cudaMemsetAsync(c->st.meta, 0, (c->st.meta_mask + 1) * sizeof(MetaSlot), s));
     CU(c, cudaMemsetAsync(c->st.issuer_counts, 0, c->st.max_issuers * sizeof(unsigned long long), s));
     CU(c, cudaMemsetAsync(c->small_dev + 64, 0, 16 * sizeof(unsigned long long), s));
     return CTMR_OK;
@@ -655,6 +685,14 @@ int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets
         dout.serial_off = s.serial_off;
         dout.serial_len = s.serial_len;
         dout.keys = s.keys;
+        const bool want_meta = out->first_issuer_dn || out->first_crldp || out->issuer_name_off || out->crldp_off;
+        const uint64_t E = c->stage_entries;
+        if (want_meta) {
+            dout.issuer_name_off = s.spans;
+            dout.issuer_name_len = s.spans + E;
+            dout.crldp_off = s.spans + 2 * E;
+            dout.crldp_len = s.spans + 3 * E;
+        }
         MapParams p;
         fill_map_params(c, &db, &dout, p, sub % kStages, c->fuse_insert ? s.slot_of : nullptr);
         if (c->bucket_by_length && cnt > 64 && p.sha256) {
@@ -669,6 +707,16 @@ int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets
         CU(c, cudaEventRecord(s.reduced, s.stream));
         prev = s.reduced;
         CU(c, launch_resolve_pairs(c->st, s.keys, cnt, s.pair_slot, s.was_unknown, s.first, s.stream));
+        if (want_meta) {
+            CU(c, launch_meta(c->st, db.blob, s.offsets, s.keys, cnt, s.was_unknown, dout.issuer_name_off, dout.issuer_name_len,
+                              dout.crldp_off, dout.crldp_len, s.meta_slots, s.first_meta, s.first_meta + E, s.stream));
+            if (out->issuer_name_off) CU(c, cudaMemcpyAsync(out->issuer_name_off + lo, dout.issuer_name_off, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+            if (out->issuer_name_len) CU(c, cudaMemcpyAsync(out->issuer_name_len + lo, dout.issuer_name_len, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+            if (out->crldp_off) CU(c, cudaMemcpyAsync(out->crldp_off + lo, dout.crldp_off, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+            if (out->crldp_len) CU(c, cudaMemcpyAsync(out->crldp_len + lo, dout.crldp_len, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+            if (out->first_issuer_dn) CU(c, cudaMemcpyAsync(out->first_issuer_dn + lo, s.first_meta, cnt, cudaMemcpyDeviceToHost, s.stream));
+            if (out->first_crldp) CU(c, cudaMemcpyAsync(out->first_crldp + lo, s.first_meta + E, cnt, cudaMemcpyDeviceToHost, s.stream));
+        }
         if (out->status) CU(c, cudaMemcpyAsync(out->status + lo, s.status, cnt, cudaMemcpyDeviceToHost, s.stream));
         if (out->sha256) CU(c, cudaMemcpyAsync(out->sha256 + lo * 32, s.sha, cnt * 32, cudaMemcpyDeviceToHost, s.stream));
         if (out->exp_hour) CU(c, cudaMemcpyAsync(out->exp_hour + lo, s.exp_hour, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
@@ -734,14 +782,15 @@ int ctmr_preload_known(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], 
 
 namespace {
 struct SnapHeader {
-    char magic[8];  // "CTMRSNP1"
-    uint64_t table_slots, pair_slots, max_issuers, n_issuers, next_index;
+    char magic[8];  // "CTMRSNP2"
+    uint64_t table_slots, pair_slots, meta_slots, max_issuers, n_issuers, next_index;
 };
 }  // namespace
 
 int ctmr_snapshot_size(ctmr_ctx* c, uint64_t* bytes) {
     if (!c || !bytes) return fail(c, CTMR_E_INVALID, "bad argument");
     *bytes = sizeof(SnapHeader) + (c->st.table_mask + 1) * sizeof(KnownSlot) + (c->st.pair_mask + 1) * sizeof(PairSlot) +
+             (c->st.meta_mask + 1) * sizeof(MetaSlot) +
              c->st.max_issuers * sizeof(uint64_t) + CTMR_ST__COUNT * sizeof(uint64_t) + c->digests.size() * 32;
     return CTMR_OK;
 }
@@ -754,9 +803,10 @@ int ctmr_snapshot_save(ctmr_ctx* c, uint8_t* buf, uint64_t cap, uint64_t* writte
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaDeviceSynchronize());
     SnapHeader h{};
-    std::memcpy(h.magic, "CTMRSNP1", 8);
+    std::memcpy(h.magic, "CTMRSNP2", 8);
     h.table_slots = c->st.table_mask + 1;
     h.pair_slots = c->st.pair_mask + 1;
+    h.meta_slots = c->st.meta_mask + 1;
     h.max_issuers = c->st.max_issuers;
     h.n_issuers = c->digests.size();
     h.next_index = c->next_index;
@@ -764,6 +814,7 @@ int ctmr_snapshot_save(ctmr_ctx* c, uint8_t* buf, uint64_t cap, uint64_t* writte
     std::memcpy(p, &h, sizeof h); p += sizeof h;
     CU(c, cudaMemcpy(p, c->st.table, h.table_slots * sizeof(KnownSlot), cudaMemcpyDeviceToHost)); p += h.table_slots * sizeof(KnownSlot);
     CU(c, cudaMemcpy(p, c->st.pairs, h.pair_slots * sizeof(PairSlot), cudaMemcpyDeviceToHost)); p += h.pair_slots * sizeof(PairSlot);
+    CU(c, cudaMemcpy(p, c->st.meta, h.meta_slots * sizeof(MetaSlot), cudaMemcpyDeviceToHost)); p += h.meta_slots * sizeof(MetaSlot);
     CU(c, cudaMemcpy(p, c->st.issuer_counts, h.max_issuers * sizeof(uint64_t), cudaMemcpyDeviceToHost)); p += h.max_issuers * sizeof(uint64_t);
     CU(c, cudaMemcpy(p, c->st.status_counts, CTMR_ST__COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost)); p += CTMR_ST__COUNT * sizeof(uint64_t);
     for (const auto& d : c->digests) { std::memcpy(p, d.data(), 32); p += 32; }
@@ -775,17 +826,19 @@ int ctmr_snapshot_load(ctmr_ctx* c, const uint8_t* buf, uint64_t bytes) {
     if (!c || !buf || bytes < sizeof(SnapHeader)) return fail(c, CTMR_E_INVALID, "bad snapshot");
     SnapHeader h;
     std::memcpy(&h, buf, sizeof h);
-    if (std::memcmp(h.magic, "CTMRSNP1", 8) != 0) return fail(c, CTMR_E_INVALID, "not a ctmr snapshot");
-    if (h.table_slots != c->st.table_mask + 1 || h.pair_slots != c->st.pair_mask + 1 || h.max_issuers != c->st.max_issuers)
+    if (std::memcmp(h.magic, "CTMRSNP2", 8) != 0) return fail(c, CTMR_E_INVALID, "not a ctmr snapshot");
+    if (h.table_slots != c->st.table_mask + 1 || h.pair_slots != c->st.pair_mask + 1 || h.meta_slots != c->st.meta_mask + 1 ||
+        h.max_issuers != c->st.max_issuers)
         return fail(c, CTMR_E_INVALID, "snapshot was taken with different capacities (table / pairs / max_issuers)");
     const uint64_t need = sizeof h + h.table_slots * sizeof(KnownSlot) + h.pair_slots * sizeof(PairSlot) +
-                          h.max_issuers * sizeof(uint64_t) + CTMR_ST__COUNT * sizeof(uint64_t) + h.n_issuers * 32;
+                          h.meta_slots * sizeof(MetaSlot) + h.max_issuers * sizeof(uint64_t) + CTMR_ST__COUNT * sizeof(uint64_t) + h.n_issuers * 32;
     if (bytes < need || h.n_issuers > h.max_issuers) return fail(c, CTMR_E_INVALID, "truncated snapshot");
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaDeviceSynchronize());
     const uint8_t* p = buf + sizeof h;
     CU(c, cudaMemcpy(c->st.table, p, h.table_slots * sizeof(KnownSlot), cudaMemcpyHostToDevice)); p += h.table_slots * sizeof(KnownSlot);
     CU(c, cudaMemcpy(c->st.pairs, p, h.pair_slots * sizeof(PairSlot), cudaMemcpyHostToDevice)); p += h.pair_slots * sizeof(PairSlot);
+    CU(c, cudaMemcpy(c->st.meta, p, h.meta_slots * sizeof(MetaSlot), cudaMemcpyHostToDevice)); p += h.meta_slots * sizeof(MetaSlot);
     CU(c, cudaMemcpy(c->st.issuer_counts, p, h.max_issuers * sizeof(uint64_t), cudaMemcpyHostToDevice)); p += h.max_issuers * sizeof(uint64_t);
     CU(c, cudaMemcpy(c->st.status_counts, p, CTMR_ST__COUNT * sizeof(uint64_t), cudaMemcpyHostToDevice)); p += CTMR_ST__COUNT * sizeof(uint64_t);
     c->digests.clear();

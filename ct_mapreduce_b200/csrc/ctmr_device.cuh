@@ -245,6 +245,7 @@ struct ParsedCert {
     uint32_t cn_off, cn_len;       // issuer CommonName value octets (cn_len = 0 and !has_cn -> "")
     uint32_t spki_off, spki_len;   // RawSubjectPublicKeyInfo, full TLV
     uint32_t crldp_off, crldp_len; // cRLDistributionPoints extnValue content, 0 = absent
+    uint32_t issuer_off, issuer_len; // issuer Name, full TLV
     int64_t not_after;             // unix seconds
     uint32_t flags;                // PC_*
 };
@@ -384,6 +385,7 @@ __device__ inline bool der_name(const uint8_t* __restrict__ d, uint32_t pos, uin
 __device__ inline bool parse_cert(const uint8_t* __restrict__ d, uint32_t len, ParsedCert& pc) {
     pc.serial_off = pc.serial_len = pc.cn_off = pc.cn_len = 0;
     pc.spki_off = pc.spki_len = pc.crldp_off = pc.crldp_len = 0;
+    pc.issuer_off = pc.issuer_len = 0;
     pc.not_after = 0;
     pc.flags = 0;
     Tlv cert, tbs, t;
@@ -407,6 +409,8 @@ __device__ inline bool parse_cert(const uint8_t* __restrict__ d, uint32_t len, P
     if (!der_read(d, tp, tend, t) || t.tag != 0x30u) return false;  // signature AlgorithmIdentifier
     tp += t.hdr + t.len;
     if (!der_read(d, tp, tend, t) || t.tag != 0x30u) return false;  // issuer
+    pc.issuer_off = tp;
+    pc.issuer_len = t.hdr + t.len;
     if (!der_name(d, tp + t.hdr, tp + t.hdr + t.len, &pc)) return false;
     tp += t.hdr + t.len;
     if (!der_read(d, tp, tend, t) || t.tag != 0x30u) return false;  // validity

@@ -393,11 +393,19 @@ __global__ void __launch_bounds__(256, 4) map_light_kernel(const __grid_constant
             }
         } else {
             pc.serial_off = pc.serial_len = 0;
+            pc.issuer_off = pc.issuer_len = pc.crldp_off = pc.crldp_len = 0;
         }
         if (p.status) p.status[e] = (uint8_t)status;
         if (p.exp_hour) p.exp_hour[e] = exp_hour;
         if (p.serial_off) p.serial_off[e] = pc.serial_off;
         if (p.serial_len) p.serial_len[e] = pc.serial_len;
+        if (p.issuer_name_off) {
+            const bool okp = status != CTMR_ST_PARSE_ERR;
+            p.issuer_name_off[e] = okp ? pc.issuer_off : 0u;
+            p.issuer_name_len[e] = okp ? pc.issuer_len : 0u;
+            p.crldp_off[e] = okp ? pc.crldp_off : 0u;
+            p.crldp_len[e] = okp ? pc.crldp_len : 0u;
+        }
         if (p.keys) {
             const bool valid = status == CTMR_ST_OK;
             uint32_t body[12];
@@ -642,6 +650,13 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
             if (p.exp_hour) p.exp_hour[e] = exp_hour;
             if (p.serial_off) p.serial_off[e] = serial_off;
             if (p.serial_len) p.serial_len[e] = serial_len;
+            if (p.issuer_name_off) {  // spans of the strings IssuerMetadata.Accumulate looks at
+                const bool okp = w.st == W_DONE;
+                p.issuer_name_off[e] = okp ? w.name_off : 0u;
+                p.issuer_name_len[e] = okp ? w.name_len : 0u;
+                p.crldp_off[e] = okp ? w.crldp_off : 0u;
+                p.crldp_len[e] = okp ? w.crldp_len : 0u;
+            }
             if (p.keys) {
                 const bool valid = status == CTMR_ST_OK;
                 const uint64_t gi = p.first_index + e;
@@ -1098,7 +1113,98 @@ __global__ void __launch_bounds__(256) pairs_kernel(DeviceState st, const ctmr_k
     first_issuer_hour[j] = first;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K_meta: IssuerMetadata's string reducers (storage/issuermetadata.go:92-138).  For every NEW
+// certificate the reference looks up the issuer DN and each CRL distribution point in per-issuer
+// memo sets and only on a miss talks to Redis.  Here the (issuer, bytes) identity of the raw issuer
+// Name and of the raw cRLDistributionPoints value is inserted into a device table (two independent
+// 64-bit hashes; lowest index wins), so the host formats / parses those strings only for the
+// first-seen candidates.  Raw-bytes identity is finer than the reference's string identity, so the
+// candidate set is a superset of the reference's misses: nothing new can be hidden.
+// ------------------------------------------------------------------------------------------------
+__device__ inline void hash_bytes(const uint8_t* __restrict__ p, uint32_t len, uint64_t seed, uint64_t& h1, uint64_t& h2) {
+    uint64_t a = seed ^ 0x9E3779B97F4A7C15ull, b = seed * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull;
+    for (uint32_t i = 0; i < len; i += 8) {
+        uint64_t v = 0;
+        const uint32_t n = len - i < 8u ? len - i : 8u;
+        for (uint32_t k = 0; k < n; ++k) v |= (uint64_t)__ldg(p + i + k) << (8 * k);
+        a = mix64(a ^ v) + 0x632BE59BD9B4E019ull;
+        b = mix64(b + v * 0xFF51AFD7ED558CCDull) ^ (v >> 17);
+    }
+    h1 = mix64(a ^ len) | 1ull;
+    h2 = mix64(b + len) | 1ull;
+}
+
+__device__ inline uint32_t meta_insert(const DeviceState& st, uint64_t h1, uint64_t h2, unsigned long long inv_idx) {
+    uint64_t pos = (h1 >> 5) & st.meta_mask;
+    for (uint32_t probes = 0; probes < 4096u; ++probes) {
+        MetaSlot* sl = st.meta + pos;
+        unsigned long long c1 = ld_volatile_u64(&sl->h1);
+        if (c1 == 0ull) c1 = atomicCAS(&sl->h1, 0ull, (unsigned long long)h1);
+        if (c1 == 0ull || c1 == h1) {
+            unsigned long long c2 = ld_volatile_u64(&sl->h2);
+            if (c2 == 0ull) c2 = atomicCAS(&sl->h2, 0ull, (unsigned long long)h2);  // first writer publishes; equal strings write equal values
+            if (c2 == 0ull || c2 == h2) {
+                atomicMax(&sl->inv_first, inv_idx);
+                return (uint32_t)pos;
+            }
+        }
+        pos = (pos + 1) & st.meta_mask;
+    }
+    atomicExch(st.error_flag, CTMR_E_TABLE_FULL);
+    return 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(256) meta_insert_kernel(DeviceState st, const uint8_t* __restrict__ blob,
+                                                          const uint64_t* __restrict__ offsets, const ctmr_key* __restrict__ keys,
+                                                          uint64_t m, const uint8_t* __restrict__ was_unknown,
+                                                          const uint32_t* __restrict__ name_off, const uint32_t* __restrict__ name_len,
+                                                          const uint32_t* __restrict__ crl_off, const uint32_t* __restrict__ crl_len,
+                                                          uint32_t* __restrict__ meta_slots) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    uint32_t s_dn = 0xFFFFFFFFu, s_crl = 0xFFFFFFFFu;
+    if (was_unknown[j]) {
+        const uint4 q0 = reinterpret_cast<const uint4*>(keys + j)[0];
+        const unsigned long long inv_idx = ~(((unsigned long long)q0.y << 32) | q0.x);
+        const uint8_t* d = blob + offsets[j];
+        uint64_t h1, h2;
+        if (name_len[j]) {
+            hash_bytes(d + name_off[j], name_len[j], ((uint64_t)q0.w << 8) | 1u, h1, h2);
+            s_dn = meta_insert(st, h1, h2, inv_idx);
+        }
+        if (crl_len[j]) {
+            hash_bytes(d + crl_off[j], crl_len[j], ((uint64_t)q0.w << 8) | 2u, h1, h2);
+            s_crl = meta_insert(st, h1, h2, inv_idx);
+        }
+    }
+    meta_slots[2 * j] = s_dn;
+    meta_slots[2 * j + 1] = s_crl;
+}
+
+__global__ void __launch_bounds__(256) meta_resolve_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
+                                                           const uint32_t* __restrict__ meta_slots, uint8_t* __restrict__ first_dn,
+                                                           uint8_t* __restrict__ first_crl) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint4 q0 = reinterpret_cast<const uint4*>(keys + j)[0];
+    const unsigned long long inv_idx = ~(((unsigned long long)q0.y << 32) | q0.x);
+    const uint32_t a = meta_slots[2 * j], b = meta_slots[2 * j + 1];
+    if (first_dn) first_dn[j] = (a != 0xFFFFFFFFu && st.meta[a].inv_first == inv_idx) ? 1 : 0;
+    if (first_crl) first_crl[j] = (b != 0xFFFFFFFFu && st.meta[b].inv_first == inv_idx) ? 1 : 0;
+}
+
 static inline unsigned blocks_for(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+cudaError_t launch_meta(const DeviceState& st, const uint8_t* blob, const uint64_t* offsets, const ctmr_key* keys, uint64_t m,
+                        const uint8_t* was_unknown, const uint32_t* name_off, const uint32_t* name_len, const uint32_t* crl_off,
+                        const uint32_t* crl_len, uint32_t* meta_slots, uint8_t* first_dn, uint8_t* first_crl, cudaStream_t s) {
+    if (!m) return cudaSuccess;
+    meta_insert_kernel<<<blocks_for(m, 256), 256, 0, s>>>(st, blob, offsets, keys, m, was_unknown, name_off, name_len, crl_off,
+                                                          crl_len, meta_slots);
+    meta_resolve_kernel<<<blocks_for(m, 256), 256, 0, s>>>(st, keys, m, meta_slots, first_dn, first_crl);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_insert(const DeviceState& st, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, cudaStream_t s) {
     if (!m) return cudaSuccess;

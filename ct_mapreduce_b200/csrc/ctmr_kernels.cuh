@@ -31,6 +31,13 @@ struct __align__(16) PairSlot {
     unsigned long long inv_first;  // ~(lowest index among was-unknown entries of this (issuer, hour))
 };
 
+struct __align__(16) MetaSlot {      // IssuerMetadata string sets: identity = two independent 64-bit hashes
+    unsigned long long h1;           // 0 = empty
+    unsigned long long h2;           // 0 = not yet published
+    unsigned long long inv_first;    // ~(lowest index among new certificates carrying this string)
+    unsigned long long pad;
+};
+
 struct DeviceState {
     KnownSlot* table;
     uint64_t table_mask;       // capacity - 1
@@ -41,6 +48,8 @@ struct DeviceState {
     unsigned long long* status_counts;  // [CTMR_ST__COUNT]
     unsigned long long* slots_used;     // [1]
     int* error_flag;                    // [1]: 0 ok, CTMR_E_TABLE_FULL...
+    MetaSlot* meta;                     // (issuer, kind, bytes) first-seen table
+    uint64_t meta_mask;
 };
 
 struct MapParams {
@@ -63,6 +72,10 @@ struct MapParams {
     uint32_t* serial_off;
     uint32_t* serial_len;
     ctmr_key* keys;
+    uint32_t* issuer_name_off;
+    uint32_t* issuer_name_len;
+    uint32_t* crldp_off;
+    uint32_t* crldp_len;
     unsigned long long* status_counts;
     unsigned long long* work_counter;  // [1] scratch of the dynamically scheduled map kernel
     const uint32_t* order;             // [n] length-bucketed processing order (NULL = entry order)
@@ -82,6 +95,10 @@ cudaError_t launch_resolve(const DeviceState& st, const ctmr_key* keys, uint64_t
                            uint32_t* pair_slot, uint8_t* was_unknown, cudaStream_t s);
 cudaError_t launch_resolve_pairs(const DeviceState& st, const ctmr_key* keys, uint64_t m, const uint32_t* pair_slot,
                                  const uint8_t* was_unknown, uint8_t* first_issuer_hour, cudaStream_t s);
+cudaError_t launch_meta(const DeviceState& st, const uint8_t* blob, const uint64_t* offsets, const ctmr_key* keys, uint64_t m,
+                        const uint8_t* was_unknown, const uint32_t* name_off, const uint32_t* name_len, const uint32_t* crl_off,
+                        const uint32_t* crl_len, uint32_t* meta_slots /* [2*m] scratch */, uint8_t* first_dn, uint8_t* first_crl,
+                        cudaStream_t s);
 cudaError_t launch_issuer_prepare(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint8_t* digests,
                                   uint8_t* ok, cudaStream_t s);
 cudaError_t launch_table_count(const DeviceState& st, unsigned long long* out, cudaStream_t s);

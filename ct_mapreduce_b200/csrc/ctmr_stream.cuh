@@ -36,11 +36,14 @@ struct Walker {
     uint32_t end_tbs, end_b, end_c, end_d;  // tbs | name or extensions | set, validity, spki or extension | atv or bc value
     uint32_t which;                          // last arc of a 2.5.29.x extension OID, 0 otherwise
     uint32_t serial_off, serial_len;
+    uint32_t name_off, name_len;    // issuer Name, full TLV
+    uint32_t crldp_off, crldp_len;  // cRLDistributionPoints extnValue content
     int64_t not_after;
 
     __device__ __forceinline__ void init() {
         pos = 0; st = W_CERT; flags = 0; end_tbs = end_b = end_c = end_d = 0; which = 0;
         serial_off = serial_len = 0; not_after = 0;
+        name_off = name_len = crldp_off = crldp_len = 0;
     }
 };
 
@@ -241,6 +244,7 @@ __device__ inline void walk_advance(Walker& w, const R& rd, const F& far, uint32
             break;
         case W_NAME:  // issuer, then (WF_IN_SUBJECT) subject
             if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
+            if (!(w.flags & WF_IN_SUBJECT)) { w.name_off = w.pos; w.name_len = t.hdr + t.len; }
             w.pos += t.hdr;
             w.end_b = w.pos + t.len;
             w.st = w.pos < w.end_b ? W_RDN : ((w.flags & WF_IN_SUBJECT) ? W_SPKI : W_VALIDITY);
@@ -393,6 +397,7 @@ __device__ inline void walk_advance(Walker& w, const R& rd, const F& far, uint32
                 w.end_d = w.pos + t.len;
                 w.st = W_BC_SEQ;
             } else {
+                if (w.which == 0x1fu) { w.crldp_off = w.pos + t.hdr; w.crldp_len = t.len; }  // cRLDistributionPoints
                 w.pos = w.end_c;
                 if (w.pos < w.end_b) w.st = W_EXT;
                 else { w.pos = w.end_tbs; w.st = W_SIGALG2; }

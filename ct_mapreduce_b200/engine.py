@@ -34,6 +34,13 @@ class BatchResult:
     serial_len: np.ndarray
     was_unknown: np.ndarray
     first_issuer_hour: np.ndarray
+    # IssuerMetadata string reducers (only filled by store_batch(..., want_meta=True))
+    issuer_name_off: np.ndarray | None = None
+    issuer_name_len: np.ndarray | None = None
+    crldp_off: np.ndarray | None = None
+    crldp_len: np.ndarray | None = None
+    first_issuer_dn: np.ndarray | None = None
+    first_crldp: np.ndarray | None = None
 
 
 class KnownCertificatesView:
@@ -122,7 +129,7 @@ class GpuCertDatabase:
 
     # ------------------------------------------------------------------ the hot path, host buffers
     def store_batch(self, blob, offsets, issuer_blob, issuer_offsets, issuer_idx, now_unix_ns: int,
-                    want_sha: bool = True, out: BatchResult | None = None) -> BatchResult:
+                    want_sha: bool = True, out: BatchResult | None = None, want_meta: bool = False) -> BatchResult:
         """One batch through ctmr_process_batch (HOST buffers in, HOST buffers out)."""
         blob = np.ascontiguousarray(blob, np.uint8)
         offsets = np.ascontiguousarray(offsets, np.uint64)
@@ -137,9 +144,15 @@ class GpuCertDatabase:
         if out is None:
             out = BatchResult(np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8) if want_sha else None, np.zeros(n, np.int64),
                               np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.uint8))
+        if want_meta and out.first_issuer_dn is None:
+            out.issuer_name_off, out.issuer_name_len = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+            out.crldp_off, out.crldp_len = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+            out.first_issuer_dn, out.first_crldp = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
         o = capi.Out(capi.ptr(out.status), capi.ptr(out.sha256) if want_sha else None, capi.ptr(out.exp_hour),
                      capi.ptr(out.serial_off), capi.ptr(out.serial_len), capi.ptr(out.was_unknown),
-                     capi.ptr(out.first_issuer_hour))
+                     capi.ptr(out.first_issuer_hour),
+                     *([capi.ptr(out.issuer_name_off), capi.ptr(out.issuer_name_len), capi.ptr(out.crldp_off),
+                        capi.ptr(out.crldp_len), capi.ptr(out.first_issuer_dn), capi.ptr(out.first_crldp)] if want_meta else [None] * 6))
         self._check(self._lib.ctmr_process_batch(self._h, capi.ptr(blob), capi.ptr(offsets), n,
                                                  capi.ptr(issuer_blob) if n_iss else None,
                                                  capi.ptr(issuer_offsets) if n_iss else None, n_iss,

@@ -95,6 +95,14 @@ typedef struct ctmr_out {
     uint32_t* serial_len;       /*   offset inside the entry's DER, and length                          */
     uint8_t* was_unknown;       /* KnownCertificates.WasUnknown result, storage/knowncertificates.go:38-55 */
     uint8_t* first_issuer_hour; /* 1 iff Accumulate would return seenExpDateBefore == false (issuermetadata.go:95-108) */
+    /* IssuerMetadata's string reducers: spans of the two strings Accumulate looks at, and
+     * first-seen bits so that the host only formats / parses them for candidates, not for every new certificate */
+    uint32_t* issuer_name_off;  /* issuer Name (full TLV) inside the entry's DER: source of Issuer.String() (issuermetadata.go:94) */
+    uint32_t* issuer_name_len;
+    uint32_t* crldp_off;        /* cRLDistributionPoints extnValue content (issuermetadata.go:111), len 0 = absent */
+    uint32_t* crldp_len;
+    uint8_t* first_issuer_dn;   /* 1 iff was_unknown and no earlier new certificate of this issuer had the same Name bytes */
+    uint8_t* first_crldp;       /* 1 iff was_unknown, extension present, and its bytes are new for this issuer */
 } ctmr_out;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -193,6 +201,12 @@ typedef struct ctmr_dev_out { /* device pointers, each [n]; NULL = not produced 
     uint8_t* was_unknown;
     uint8_t* first_issuer_hour;
     ctmr_key* keys; /* [n] key records (valid=0 for entries that did not reach Store) */
+    uint32_t* issuer_name_off; /* as in ctmr_out; first_* are produced by ctmr_process_device only */
+    uint32_t* issuer_name_len;
+    uint32_t* crldp_off;
+    uint32_t* crldp_len;
+    uint8_t* first_issuer_dn;
+    uint8_t* first_crldp;
 } ctmr_dev_out;
 
 /* map half: DER walk + filter + SHA-256 -> status, exp_hour, serial span, fingerprint, key records */

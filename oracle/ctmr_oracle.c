@@ -561,6 +561,7 @@ struct ora_db {
     uint8_t* filter; size_t filter_len; int log_expired;
     ora_cache* cache;
     bs_map issuer_hours;  /* IssuerMetadata.knownExpDates across all issuers: key = digest||exp_hour */
+    bs_map issuer_strings; /* knownIssuerDNs / knownCrlDPs by raw bytes: key = digest||kind||bytes */
     bs_map set_meta;      /* set key -> index into metas */
     struct { uint8_t digest[32]; int64_t exp_hour; char key[160]; uint32_t key_len; }* metas;
     uint64_t n_metas, cap_metas;
@@ -573,12 +574,12 @@ ora_db* ora_db_new(const uint8_t* filter, size_t flen, int log_expired) {
     if (flen) memcpy(db->filter, filter, flen);
     db->filter_len = flen; db->log_expired = log_expired;
     db->cache = ora_cache_new();
-    bs_init(&db->issuer_hours); bs_init(&db->set_meta);
+    bs_init(&db->issuer_hours); bs_init(&db->set_meta); bs_init(&db->issuer_strings);
     return db;
 }
 void ora_db_free(ora_db* db) {
     if (!db) return;
-    ora_cache_free(db->cache); bs_free(&db->issuer_hours); bs_free(&db->set_meta);
+    ora_cache_free(db->cache); bs_free(&db->issuer_hours); bs_free(&db->set_meta); bs_free(&db->issuer_strings);
     free(db->metas); free(db->filter); free(db);
 }
 
@@ -586,6 +587,7 @@ typedef struct {
     const uint8_t* blob; const uint64_t* offsets; uint64_t lo, hi;
     const uint8_t* filter; size_t flen; int log_expired; int64_t now_ns;
     uint8_t* status; uint8_t* sha; int64_t* exp_hour; uint32_t* soff; uint32_t* slen; uint64_t kept;
+    uint32_t *noff, *nlen, *coff, *clen;
 } map_job;
 
 /* map half of insertCTWorker (ct-fetch.go:198-213) + the whole-certificate fingerprint */
@@ -600,9 +602,11 @@ static void* map_worker(void* arg) {
         if (ora_parse_cert(der, len, &c)) {
             st = ORA_ST_PARSE_ERR;
             if (j->exp_hour) { j->exp_hour[i] = 0; j->soff[i] = 0; j->slen[i] = 0; }
+            if (j->noff) { j->noff[i] = j->nlen[i] = j->coff[i] = j->clen[i] = 0; }
         } else {
             st = ora_filter(der, &c, j->filter, j->flen, j->log_expired, j->now_ns);
             if (j->exp_hour) { j->exp_hour[i] = ora_exp_hour(c.not_after); j->soff[i] = c.serial_off; j->slen[i] = c.serial_len; }
+            if (j->noff) { j->noff[i] = c.issuer_off; j->nlen[i] = c.issuer_len; j->coff[i] = c.crldp_off; j->clen[i] = c.crldp_len; }
         }
         if (j->status) j->status[i] = (uint8_t)st;
         if (st == 0) j->kept++;
@@ -653,12 +657,16 @@ int ora_db_process(ora_db* db, const uint8_t* blob, const uint64_t* offsets, uin
     p.blob = blob; p.offsets = offsets; p.filter = db->filter; p.flen = db->filter_len;
     p.log_expired = db->log_expired; p.now_ns = now_ns;
     p.status = out->status; p.sha = out->sha256; p.exp_hour = out->exp_hour; p.soff = out->serial_off; p.slen = out->serial_len;
+    const int meta = out->issuer_name_off && out->issuer_name_len && out->crldp_off && out->crldp_len;
+    if (meta) { p.noff = out->issuer_name_off; p.nlen = out->issuer_name_len; p.coff = out->crldp_off; p.clen = out->crldp_len; }
     run_map(&p, n, nthreads);
 
     /* reduce half, strictly sequential = numThreads 1 (config/config.go:187) */
     for (uint64_t i = 0; i < n; ++i) {
         out->was_unknown[i] = 0;
         out->first_issuer_hour[i] = 0;
+        if (meta && out->first_issuer_dn) out->first_issuer_dn[i] = 0;
+        if (meta && out->first_crldp) out->first_crldp[i] = 0;
         int st = out->status[i];
         if (st == 0) {
             uint32_t k = issuer_idx[i];
@@ -696,6 +704,23 @@ int ora_db_process(ora_db* db, const uint8_t* blob, const uint64_t* offsets, uin
             int first;
             bs_put(&db->issuer_hours, ih, 40, &first);
             out->first_issuer_hour[i] = (uint8_t)first;
+            if (meta) {
+                /* Accumulate's memo lookups for the issuer DN (issuermetadata.go:94,130-135) and the CRL
+                 * distribution points (:110-128), on the raw bytes those strings are formatted from */
+                const uint8_t* der = blob + offsets[i];
+                for (int kind = 1; kind <= 2; ++kind) {
+                    const uint32_t so = kind == 1 ? out->issuer_name_off[i] : out->crldp_off[i];
+                    const uint32_t sl = kind == 1 ? out->issuer_name_len[i] : out->crldp_len[i];
+                    uint8_t* dstbit = kind == 1 ? out->first_issuer_dn : out->first_crldp;
+                    if (!sl || !dstbit) continue;
+                    uint8_t* kb = (uint8_t*)malloc(33 + sl);
+                    memcpy(kb, is->digest, 32); kb[32] = (uint8_t)kind; memcpy(kb + 33, der + so, sl);
+                    int fresh;
+                    bs_put(&db->issuer_strings, kb, 33 + sl, &fresh);
+                    dstbit[i] = (uint8_t)fresh;
+                    free(kb);
+                }
+            }
         }
     }
     free(irec);

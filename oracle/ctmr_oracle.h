@@ -97,6 +97,13 @@ typedef struct ora_out {
     uint32_t* serial_len;     /* [n] */
     uint8_t* was_unknown;     /* [n] knowncertificates.go:38-55 */
     uint8_t* first_issuer_hour; /* [n] !seenExpDateBefore, issuermetadata.go:95-108 */
+    /* IssuerMetadata string reducers (issuermetadata.go:110-135), may be NULL as a group */
+    uint32_t* issuer_name_off;  /* [n] issuer Name TLV span */
+    uint32_t* issuer_name_len;
+    uint32_t* crldp_off;        /* [n] cRLDistributionPoints extnValue content span */
+    uint32_t* crldp_len;
+    uint8_t* first_issuer_dn;   /* [n] new certificate whose (issuer, Name bytes) was not seen on an earlier new certificate */
+    uint8_t* first_crldp;       /* [n] same for (issuer, cRLDistributionPoints bytes) */
 } ora_out;
 
 /* issuer_idx[i] == 0xFFFFFFFF means len(Chain) < 1.  nthreads>1 parallelises the map half only. */

@@ -49,7 +49,9 @@ class OraCert(C.Structure):
 
 class OraOut(C.Structure):
     _fields_ = [("status", C.c_void_p), ("sha256", C.c_void_p), ("exp_hour", C.c_void_p), ("serial_off", C.c_void_p),
-                ("serial_len", C.c_void_p), ("was_unknown", C.c_void_p), ("first_issuer_hour", C.c_void_p)]
+                ("serial_len", C.c_void_p), ("was_unknown", C.c_void_p), ("first_issuer_hour", C.c_void_p),
+                ("issuer_name_off", C.c_void_p), ("issuer_name_len", C.c_void_p), ("crldp_off", C.c_void_p),
+                ("crldp_len", C.c_void_p), ("first_issuer_dn", C.c_void_p), ("first_crldp", C.c_void_p)]
 
 
 def build(force: bool = False) -> str:
@@ -215,6 +217,12 @@ class Result:
         self.serial_len = np.zeros(n, np.uint32)
         self.was_unknown = np.zeros(n, np.uint8)
         self.first_issuer_hour = np.zeros(n, np.uint8)
+        self.issuer_name_off = np.zeros(n, np.uint32)
+        self.issuer_name_len = np.zeros(n, np.uint32)
+        self.crldp_off = np.zeros(n, np.uint32)
+        self.crldp_len = np.zeros(n, np.uint32)
+        self.first_issuer_dn = np.zeros(n, np.uint8)
+        self.first_crldp = np.zeros(n, np.uint8)
 
 
 class DB:
@@ -238,7 +246,9 @@ class DB:
         n = offsets.size - 1
         r = Result(n)
         o = OraOut(r.status.ctypes.data, r.sha256.ctypes.data, r.exp_hour.ctypes.data, r.serial_off.ctypes.data,
-                   r.serial_len.ctypes.data, r.was_unknown.ctypes.data, r.first_issuer_hour.ctypes.data)
+                   r.serial_len.ctypes.data, r.was_unknown.ctypes.data, r.first_issuer_hour.ctypes.data,
+                   r.issuer_name_off.ctypes.data, r.issuer_name_len.ctypes.data, r.crldp_off.ctypes.data,
+                   r.crldp_len.ctypes.data, r.first_issuer_dn.ctypes.data, r.first_crldp.ctypes.data)
         rc = lib().ora_db_process(self.h, _p(blob), _p(offsets), n, _p(issuer_blob), _p(issuer_offsets),
                                   issuer_offsets.size - 1, _p(issuer_idx), now_ns, nthreads, C.byref(o))
         assert rc == 0

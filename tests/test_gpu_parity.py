@@ -362,3 +362,42 @@ def test_fuzz_whole_certificate_mutations(eng, ora):
         r_gpu, r_ora, _, _, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, flt=README_FILTER, log_expired=False, flags=flags)
         assert_same(r_gpu, r_ora, sha=(flags == 0))
     assert 0 < int((r_ora.status == 1).sum()) < len(ders)  # both parsed and rejected records are present
+
+
+def test_issuer_metadata_string_reducers(eng, ora):
+    """spans of the issuer Name and the cRLDistributionPoints value, and the
+    first-seen bits that let the host run IssuerMetadata.Accumulate's string inserts only for
+    candidates (storage/issuermetadata.go:92-138).  Two batches: the sets persist."""
+    import warnings
+    from cryptography import x509
+    warnings.filterwarnings("ignore")
+    n = 6000
+    cfg = ora.synth_cfg(n, len_mode=1, len_lo=512, len_hi=4096, dup_mode=1)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    odb = ora.DB(README_FILTER, False)
+    h = 2500
+    with eng.GpuCertDatabase(issuer_cn_filter=README_FILTER, table_capacity=1 << 16) as db:
+        for lo, hi in ((0, h), (h, n)):
+            want = odb.process(blob, offs[lo:hi + 1], iblob, ioffs, idx[lo:hi], NOW_NS)
+            got = db.store_batch(blob, offs[lo:hi + 1], iblob, ioffs, idx[lo:hi], NOW_NS, want_meta=True)
+            assert_same(got, want)
+            parsed = want.status != 1
+            for f in ("issuer_name_off", "issuer_name_len", "crldp_off", "crldp_len"):
+                assert np.array_equal(getattr(got, f)[parsed], getattr(want, f)[parsed]), f
+            for f in ("first_issuer_dn", "first_crldp"):
+                bad = np.nonzero(getattr(got, f) != getattr(want, f))[0]
+                assert bad.size == 0, (f, bad[:10])
+            # candidates only among new certificates, and at most a handful per issuer
+            assert not (got.first_issuer_dn & ~got.was_unknown).any()
+            assert int(got.first_issuer_dn.sum()) <= cfg.n_issuers and int(got.first_crldp.sum()) <= 2 * cfg.n_issuers
+        # the spans are what an X.509 library calls the issuer name / the extension value
+        for i in np.nonzero(got.first_issuer_dn)[0][:20]:
+            e = h + int(i)
+            der = blob[offs[e]:offs[e + 1]].tobytes()
+            cert = x509.load_der_x509_certificate(der)
+            a, l = int(got.issuer_name_off[i]), int(got.issuer_name_len[i])
+            assert der[a:a + l] == cert.issuer.public_bytes()
+            a, l = int(got.crldp_off[i]), int(got.crldp_len[i])
+            ext = cert.extensions.get_extension_for_oid(x509.oid.ExtensionOID.CRL_DISTRIBUTION_POINTS)
+            assert ext.value[0].full_name[0].value.encode() in der[a:a + l]
