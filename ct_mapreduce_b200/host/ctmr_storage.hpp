@@ -311,6 +311,10 @@ class IssuerMetadata {  // storage/issuermetadata.go
         if (knownIssuerDNs_.insert(dn).second) return {seenExpDate, addIssuerDN(dn)};
         return {seenExpDate, ""};
     }
+    // the three memo steps of Accumulate, individually (the GPU pre-filters which ones are worth calling)
+    bool NoteExpDate(const ExpDate& e) { return !knownExpDates_.insert(e.ID()).second; }
+    Error NoteIssuerDN(const std::string& dn) { return knownIssuerDNs_.insert(dn).second ? addIssuerDN(dn) : ""; }
+    Error NoteCRL(const std::string& dp) { return knownCrlDPs_.insert(dp).second ? addCRL(dp) : ""; }
     std::vector<std::string> Issuers() const { return cache_->SetList(issuersId()).first; }
     std::vector<std::string> CRLs() const { return cache_->SetList(crlId()).first; }
 
@@ -336,9 +340,120 @@ inline std::string PemEncode(const uint8_t* der, size_t n) {
     return out + "-----END CERTIFICATE-----\n";
 }
 
+// ---------------------------------------------------------------------------------- strings of IssuerMetadata
+// Minimal DER cursor for the two host-side string extractions (only ever applied to spans the GPU
+// walker has already validated).
+struct DerTlv { uint8_t tag = 0; size_t hdr = 0, len = 0; bool ok = false; };
+inline DerTlv DerRead(const uint8_t* d, size_t pos, size_t end) {
+    DerTlv t;
+    if (pos + 2 > end) return t;
+    t.tag = d[pos];
+    const uint8_t l = d[pos + 1];
+    if (l < 0x80) { t.hdr = 2; t.len = l; }
+    else {
+        const size_t nb = l & 0x7f;
+        if (nb == 0 || nb > 4 || pos + 2 + nb > end) return t;
+        for (size_t i = 0; i < nb; ++i) t.len = (t.len << 8) | d[pos + 2 + i];
+        t.hdr = 2 + nb;
+    }
+    t.ok = pos + t.hdr + t.len <= end;
+    return t;
+}
+
+// pkix.Name.String() (issuermetadata.go:94): FillFromRDNSequence keeps the standard attribute
+// types, ToRDNSequence re-emits them grouped by type in the order C, ST, L, STREET, POSTALCODE, O,
+// OU, CN, SERIALNUMBER, and String() prints that sequence back to front, values of one type joined
+// with '+', RFC 2253 escaping.  Pinned by the reference only for a single CN
+// (issuermetadata_test.go:133 "CN=My First Issuer (tm)"); multi-attribute output follows Go's code.
+inline std::string FormatIssuerDN(const uint8_t* name, size_t n) {
+    static const struct { uint8_t arc; const char* label; } kOrder[] = {
+        {6, "C"}, {8, "ST"}, {7, "L"}, {9, "STREET"}, {17, "POSTALCODE"}, {10, "O"}, {11, "OU"}, {3, "CN"}, {5, "SERIALNUMBER"}};
+    std::map<uint8_t, std::vector<std::string>> vals;
+    DerTlv seq = DerRead(name, 0, n);
+    if (!seq.ok || seq.tag != 0x30) return "";
+    size_t pos = seq.hdr, end = seq.hdr + seq.len;
+    while (pos < end) {
+        DerTlv set = DerRead(name, pos, end);
+        if (!set.ok) break;
+        size_t sp = pos + set.hdr, se = sp + set.len;
+        while (sp < se) {
+            DerTlv atv = DerRead(name, sp, se);
+            if (!atv.ok) break;
+            const size_t ap = sp + atv.hdr, ae = ap + atv.len;
+            DerTlv oid = DerRead(name, ap, ae);
+            if (!oid.ok) break;
+            DerTlv val = DerRead(name, ap + oid.hdr + oid.len, ae);
+            const uint8_t* o = name + ap + oid.hdr;
+            const bool str = val.ok && (val.tag == 0x0c || val.tag == 0x13 || val.tag == 0x16 || val.tag == 0x14 || val.tag == 0x12);
+            if (str && oid.len == 3 && o[0] == 0x55 && o[1] == 0x04) {
+                const size_t vp = ap + oid.hdr + oid.len + val.hdr;
+                if (o[2] == 3) vals[3] = {std::string((const char*)name + vp, val.len)};  // CommonName: the last one wins
+                else vals[o[2]].push_back(std::string((const char*)name + vp, val.len));
+            }
+            sp += atv.hdr + atv.len;
+        }
+        pos += set.hdr + set.len;
+    }
+    std::string out;
+    for (int k = (int)(sizeof kOrder / sizeof kOrder[0]) - 1; k >= 0; --k) {
+        auto it = vals.find(kOrder[k].arc);
+        if (it == vals.end() || it->second.empty()) continue;
+        if (!out.empty()) out += ",";
+        for (size_t j = 0; j < it->second.size(); ++j) {
+            if (j) out += "+";
+            out += kOrder[k].label;
+            out += "=";
+            const std::string& v = it->second[j];
+            for (size_t c = 0; c < v.size(); ++c) {
+                const char ch = v[c];
+                bool esc = ch == ',' || ch == '+' || ch == '"' || ch == '\\' || ch == '<' || ch == '>' || ch == ';';
+                if (ch == ' ') esc = c == 0 || c + 1 == v.size();
+                if (ch == '#') esc = c == 0;
+                if (esc) out += '\\';
+                out += ch;
+            }
+        }
+    }
+    return out;
+}
+
+// cert.CRLDistributionPoints (issuermetadata.go:111): the URIs ([6] IA5String) of every
+// DistributionPoint.fullName in the extension value.
+inline std::vector<std::string> ExtractCrlUris(const uint8_t* v, size_t n) {
+    std::vector<std::string> out;
+    DerTlv seq = DerRead(v, 0, n);
+    if (!seq.ok || seq.tag != 0x30) return out;
+    size_t pos = seq.hdr, end = seq.hdr + seq.len;
+    while (pos < end) {
+        DerTlv dp = DerRead(v, pos, end);
+        if (!dp.ok) break;
+        size_t p1 = pos + dp.hdr, e1 = p1 + dp.len;
+        while (p1 < e1) {
+            DerTlv f = DerRead(v, p1, e1);
+            if (!f.ok) break;
+            if (f.tag == 0xa0) {  // distributionPoint [0]
+                size_t p2 = p1 + f.hdr, e2 = p2 + f.len;
+                DerTlv fn = DerRead(v, p2, e2);
+                if (fn.ok && fn.tag == 0xa0) {  // fullName [0] GeneralNames
+                    size_t p3 = p2 + fn.hdr, e3 = p3 + fn.len;
+                    while (p3 < e3) {
+                        DerTlv gn = DerRead(v, p3, e3);
+                        if (!gn.ok) break;
+                        if (gn.tag == 0x86) out.emplace_back((const char*)v + p3 + gn.hdr, gn.len);
+                        p3 += gn.hdr + gn.len;
+                    }
+                }
+            }
+            p1 += f.hdr + f.len;
+        }
+        pos += dp.hdr + dp.len;
+    }
+    return out;
+}
+
 // ---------------------------------------------------------------------------------- the database facade
 struct BatchStats {
-    uint64_t entries = 0, stored = 0, unknown = 0, cache_inserts = 0, pem_writes = 0;
+    uint64_t entries = 0, stored = 0, unknown = 0, cache_inserts = 0, pem_writes = 0, dn_formats = 0, crl_parses = 0;
     uint64_t status[CTMR_ST__COUNT] = {};
 };
 
@@ -368,8 +483,10 @@ class GpuCertDatabase {
                      const std::function<std::vector<std::string>(uint64_t)>& crl_dps = nullptr) {
         std::vector<uint8_t> status(n), unknown(n), first(n);
         std::vector<int64_t> exp_hour(n);
-        std::vector<uint32_t> soff(n), slen(n);
-        ctmr_out out{status.data(), nullptr, exp_hour.data(), soff.data(), slen.data(), unknown.data(), first.data()};
+        std::vector<uint32_t> soff(n), slen(n), noff(n), nlen(n), coff(n), clen(n);
+        std::vector<uint8_t> first_dn(n), first_crl(n);
+        ctmr_out out{status.data(), nullptr, exp_hour.data(), soff.data(), slen.data(), unknown.data(), first.data(),
+                     noff.data(), nlen.data(), coff.data(), clen.data(), first_dn.data(), first_crl.data()};
         int rc = ctmr_process_batch(ctx_, blob, offsets, n, issuer_blob, issuer_offsets, n_issuers, issuer_idx, now_unix_ns, &out);
         if (rc != CTMR_OK) return std::string("ctmr_process_batch: ") + ctmr_last_error(ctx_);  // like a Redis outage: the caller stops
         std::vector<uint32_t> dense(n_issuers);
@@ -395,10 +512,23 @@ class GpuCertDatabase {
                 auto r = kc->WasUnknown(serial);  // SADD only for entries the GPU found new
                 ++st.cache_inserts;
                 if (!ok(r.second)) return r.second;
+                // IssuerMetadata.Accumulate: the GPU says which new certificates carry a Name / CRL-DP value not
+                // seen before for this issuer; only those are formatted / parsed (its own memo stays authoritative)
                 IssuerMetadata* im = GetIssuerMetadata(issuer);
-                auto acc = im->Accumulate(expDate, issuer_dn ? issuer_dn(i) : std::string(),
-                                          crl_dps ? crl_dps(i) : std::vector<std::string>());
-                if (!ok(acc.second)) return acc.second;
+                const uint8_t* der = blob + offsets[i];
+                if (first_dn[i] || issuer_dn) {
+                    ++st.dn_formats;
+                    Error e = im->NoteIssuerDN(issuer_dn ? issuer_dn(i) : FormatIssuerDN(der + noff[i], nlen[i]));
+                    if (!ok(e)) return e;
+                }
+                if (first_crl[i] || crl_dps) {
+                    ++st.crl_parses;
+                    for (const auto& dp : crl_dps ? crl_dps(i) : ExtractCrlUris(der + coff[i], clen[i])) {
+                        Error e = im->NoteCRL(dp);
+                        if (!ok(e)) return e;
+                    }
+                }
+                im->NoteExpDate(expDate);
                 if (first[i]) {  // !issuerDateSeenBefore (filesystemdatabase.go:189-195)
                     Error e = backend_->AllocateExpDateAndIssuer(expDate, issuer);
                     if (!ok(e)) return e;

@@ -150,12 +150,19 @@ static int run_gpu(const std::string& dir, int batches) {
         if (!ok(e)) { std::fprintf(stderr, "StoreBatch: %s\n", e.c_str()); return 4; }
         total.entries += st.entries; total.stored += st.stored; total.unknown += st.unknown;
         total.cache_inserts += st.cache_inserts; total.pem_writes += st.pem_writes;
+        total.dn_formats += st.dn_formats; total.crl_parses += st.crl_parses;
     }
     std::ofstream out(dir + "/state.txt");
     out << "STATS entries " << total.entries << " stored " << total.stored << " unknown " << total.unknown << " set_insert_calls "
-        << cache.set_insert_calls << " pem_writes " << total.pem_writes << " mark_dirty_calls " << backend.mark_dirty_calls << "\n";
+        << cache.set_insert_calls << " pem_writes " << total.pem_writes << " mark_dirty_calls " << backend.mark_dirty_calls
+        << " dn_formats " << total.dn_formats << " crl_parses " << total.crl_parses << "\n";
     for (const auto& kv : cache.Data)
         for (const auto& m : kv.second) out << "SET " << kv.first << " " << hex(m) << "\n";
+    // issuer:: and crl:: members are text: also dump them readable (spaces escaped) for the pytest side
+    for (const auto& kv : cache.Data) {
+        if (kv.first.compare(0, 8, "issuer::") != 0 && kv.first.compare(0, 5, "crl::") != 0) continue;
+        for (const auto& m : kv.second) out << "STR " << kv.first << " " << hex(m) << "\n";
+    }
     for (const auto& kv : cache.Expirations) out << "EXPIRE " << kv.first << " " << kv.second << "\n";
     for (const auto& d : backend.dirty) out << "DIRTY " << d << "\n";
     for (const auto& kv : backend.issuers_by_expdate)
@@ -178,6 +185,24 @@ static int run_gpu(const std::string& dir, int batches) {
     return 0;
 }
 
+// pkix.Name.String(): order, '+' for repeated types, escaping (Go's rules; the reference pins the single-CN case)
+static void Test_FormatIssuerDN() {
+    // C=US, O=Synth CA 5, CN=" ISRG Root X5"   (leading space must be escaped)
+    const uint8_t name[] = {0x30, 0x39, 0x31, 0x0b, 0x30, 0x09, 0x06, 0x03, 0x55, 0x04, 0x06, 0x13, 0x02, 'U', 'S',
+                            0x31, 0x13, 0x30, 0x11, 0x06, 0x03, 0x55, 0x04, 0x0a, 0x13, 0x0a, 'S', 'y', 'n', 't', 'h', ' ', 'C', 'A', ' ', '5',
+                            0x31, 0x15, 0x30, 0x13, 0x06, 0x03, 0x55, 0x04, 0x03, 0x13, 0x0c, ' ', 'I', 'S', 'R', 'G', ' ', 'R', 'o', 'o', 't', ' ', 'X'};
+    CHECK(FormatIssuerDN(name, sizeof name) == "CN=\\ ISRG Root X,O=Synth CA 5,C=US");
+    const uint8_t one[] = {0x30, 0x1f, 0x31, 0x1d, 0x30, 0x1b, 0x06, 0x03, 0x55, 0x04, 0x03, 0x0c, 0x14, 'M', 'y', ' ', 'F', 'i', 'r', 's', 't', ' ',
+                           'I', 's', 's', 'u', 'e', 'r', ' ', '(', 't', 'm', ')'};
+    CHECK(FormatIssuerDN(one, sizeof one) == "CN=My First Issuer (tm)");  // issuermetadata_test.go:133
+    // cRLDistributionPoints value with one http URI
+    const char* uri = "http://crl.example/x.crl";
+    std::vector<uint8_t> v = {0x30, 0x20, 0x30, 0x1e, 0xa0, 0x1c, 0xa0, 0x1a, 0x86, 0x18};
+    v.insert(v.end(), uri, uri + 24);
+    auto uris = ExtractCrlUris(v.data(), v.size());
+    CHECK(uris.size() == 1 && uris[0] == uri);
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "cpu") {
         Test_Unknown();
@@ -186,7 +211,8 @@ int main(int argc, char** argv) {
         Test_DuplicateCRLs();
         Test_Accumulate();
         Test_Types();
-        std::puts("host cpu tests: 6 passed");
+        Test_FormatIssuerDN();
+        std::puts("host cpu tests: 7 passed");
         return 0;
     }
     if (argc >= 4 && std::string(argv[1]) == "gpu") return run_gpu(argv[2], std::atoi(argv[3]));

@@ -29,7 +29,7 @@ def host_bin(tmp_path_factory):
 def test_reference_reducer_tests_on_cpp_host(host_bin):
     r = subprocess.run([host_bin, "cpu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    assert "6 passed" in r.stdout
+    assert "7 passed" in r.stdout
 
 
 @pytest.mark.gpu
@@ -68,13 +68,31 @@ def test_store_batch_drives_remote_cache_like_the_reference(host_bin, ora, tmp_p
         if want.first_issuer_hour[i]:
             exp_alloc.add((ora.expdate_id(hour), issuer_ids[int(idx[i])]))
 
+    # IssuerMetadata string sets (issuermetadata.go:92-138): DN via pkix.Name.String(), http(s) CRL-DPs only
+    import warnings
+    from cryptography import x509
+    warnings.filterwarnings("ignore")
+    cn_of = {0: "Let's Encrypt Authority X%d", 1: "\\ ISRG Root X%d", 2: "ISRG Root X%d", 3: "Synth Trust Services CA %d"}
+    exp_str = set()
+    for i in np.nonzero(want.was_unknown)[0]:
+        k = int(idx[i])
+        iid = issuer_ids[k]
+        exp_str.add(("issuer::" + iid, ("CN=" + cn_of[k % 4] % k + ",O=Synth CA %d,C=US" % k).encode().hex()))
+        cert = x509.load_der_x509_certificate(blob[offs[i]:offs[i + 1]].tobytes())
+        dp = cert.extensions.get_extension_for_oid(x509.oid.ExtensionOID.CRL_DISTRIBUTION_POINTS).value[0].full_name[0].value
+        if dp.startswith("http"):
+            exp_str.add(("crl::" + iid, dp.encode().hex()))
+
     got_sets, got_expire, got_dirty, got_alloc, got_pemkeys, got_pems, stats = set(), {}, set(), set(), set(), {}, {}
+    got_str = set()
     for line in open(tmp_path / "state.txt"):
         f = line.rstrip("\n").split(" ")
         if f[0] == "STATS":
             stats = dict(zip(f[1::2], map(int, f[2::2])))
         elif f[0] == "SET" and f[1].startswith("serials::"):
             got_sets.add((f[1], f[2]))
+        elif f[0] == "STR":
+            got_str.add((f[1], f[2]))
         elif f[0] == "EXPIRE":
             got_expire[f[1]] = int(f[2])
         elif f[0] == "DIRTY":
@@ -87,6 +105,7 @@ def test_store_batch_drives_remote_cache_like_the_reference(host_bin, ora, tmp_p
             got_pems[f[1]] = line.rstrip("\n").split(" ", 2)[2]
     assert got_sets == exp_sets
     assert got_expire == exp_expire
+    assert got_str == exp_str
     assert got_dirty == exp_dirty
     assert got_alloc == exp_alloc
     assert got_pemkeys == set(exp_pems)
@@ -100,3 +119,5 @@ def test_store_batch_drives_remote_cache_like_the_reference(host_bin, ora, tmp_p
     n_issuers_seen = len({int(idx[i]) for i in np.nonzero(want.was_unknown)[0]})
     assert stats["set_insert_calls"] == n_unknown + n_issuers_seen < stats["stored"]
     assert stats["pem_writes"] == n_unknown
+    # the GPU's first-seen bits keep the host's string work at O(issuers), not O(new certificates)
+    assert stats["dn_formats"] == n_issuers_seen and stats["crl_parses"] <= 2 * n_issuers_seen < n_unknown
