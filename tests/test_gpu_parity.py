@@ -401,3 +401,30 @@ def test_issuer_metadata_string_reducers(eng, ora):
             a, l = int(got.crldp_off[i]), int(got.crldp_len[i])
             ext = cert.extensions.get_extension_for_oid(x509.oid.ExtensionOID.CRL_DISTRIBUTION_POINTS)
             assert ext.value[0].full_name[0].value.encode() in der[a:a + l]
+
+
+def test_time_encodings_on_device(eng, ora):
+    """Every UTCTime / GeneralizedTime form Go accepts or rejects (tests/test_oracle_properties.py), plus
+    random instants, through both map kernels: status and expiry hour must match the oracle."""
+    import datetime
+    from ct_mapreduce_b200 import capi
+    from test_oracle_properties import _cert_with_times, _fmt_utc
+    rng = np.random.default_rng(5)
+    forms = [(b"300615123045Z", 0x17), (b"3006151230Z", 0x17), (b"300615123045+0130", 0x17), (b"300615123045-0800", 0x17),
+             (b"20300615123045Z", 0x18), (b"300615123045+0000", 0x17), (b"301315123045Z", 0x17), (b"300632123045Z", 0x17),
+             (b"300615243045Z", 0x17), (b"300615126045Z", 0x17), (b"300615123060Z", 0x17), (b"300229123045Z", 0x17),
+             (b"280229123045Z", 0x17), (b"30061512304Z", 0x17), (b"300615123045", 0x17), (b"203006151230Z", 0x18),
+             (b"300615123045Z", 0x18), (b"491231235959Z", 0x17), (b"500101000000Z", 0x17), (b"00010101000000Z", 0x18),
+             (b"99991231235959Z", 0x18), (b"20300615123045+0530", 0x18), (b"19691231235959Z", 0x18)]
+    ders = [_cert_with_times(b"900101000000Z", na, na_tag=tag) for na, tag in forms]
+    for _ in range(200):
+        t = datetime.datetime(1950, 1, 1) + datetime.timedelta(seconds=int(rng.integers(0, 3155000000)))
+        ders.append(_cert_with_times(b"900101000000Z", _fmt_utc(t)))
+    blob, offs = pack(ders)
+    ca = ders[0]
+    iblob, ioffs = pack([ca])
+    idx = np.zeros(len(ders), np.uint32)
+    for flags in (0, capi.F_NO_FINGERPRINT):
+        r_gpu, r_ora, _, _, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, flt=b"", log_expired=True, flags=flags)
+        assert_same(r_gpu, r_ora, sha=(flags == 0))
+    assert int((r_ora.status == 0).sum()) > 200 and int((r_ora.status == 1).sum()) >= 10
