@@ -428,3 +428,19 @@ def test_time_encodings_on_device(eng, ora):
         r_gpu, r_ora, _, _, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, flt=b"", log_expired=True, flags=flags)
         assert_same(r_gpu, r_ora, sha=(flags == 0))
     assert int((r_ora.status == 0).sum()) > 200 and int((r_ora.status == 1).sum()) >= 10
+
+
+def test_large_certificates_three_byte_lengths(eng, ora):
+    """Certificates of 20-70 KB: DER lengths with three octets (0x83), hundreds of streaming chunks per
+    lane, the top length bucket; both kernels."""
+    from ct_mapreduce_b200 import capi
+    n = 256
+    cfg = ora.synth_cfg(n, len_mode=0, len_lo=20000, len_hi=70000, dup_mode=1)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    assert int(np.diff(offs.astype(np.int64)).max()) > 65536
+    iblob, ioffs = ora.synth_issuers(cfg)
+    for flags in (0, capi.F_NO_FINGERPRINT):
+        r_gpu, r_ora, counts, odb, _ = run_both(eng, ora, blob, offs, iblob, ioffs, idx, flags=flags)
+        assert_same(r_gpu, r_ora, sha=(flags == 0))
+        assert {k: v for k, v in counts.items() if v} == odb.issuer_counts()
+    assert int((r_ora.status == 0).sum()) > 20
