@@ -45,9 +45,18 @@ __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t one) {
     return d;
 }
 
+#ifndef CTMR_SHA_KADD_FMA
+#define CTMR_SHA_KADD_FMA 1
+#endif
+#if CTMR_SHA_KADD_FMA
+#define CTMR_SHA_HWK(h, w, k) fadd(fadd((h), (w), one), (k), one) /* K + (h + w) as two IMADs: no ALU slot at all */
+#else
+#define CTMR_SHA_HWK(h, w, k) ((h) + (w) + (k)) /* one IADD3 with the constant */
+#endif
+
 #define CTMR_SHA_ROUND(a, b, c, d, e, f, g, h, k, w)                     \
     do {                                                                 \
-        uint32_t t1_ = (h) + (w) + (k); /* one IADD3 with the constant */  \
+        uint32_t t1_ = CTMR_SHA_HWK(h, w, k);                            \
         t1_ = fadd(fadd(bsig1(e), t1_, one), ch((e), (f), (g)), one);    \
         uint32_t t2_ = fadd(bsig0(a), maj((a), (b), (c)), one);          \
         (d) = fadd((d), t1_, one);                                       \

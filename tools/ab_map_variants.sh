@@ -8,7 +8,6 @@ while read -r v; do
   [ -z "$v" ] && continue
   echo "== $W $v"; env $v $B 2>&1 | python -c "$P" || env $v $B 2>&1 | tail -5
 done <<'LIST'
-CTMR_MAP_CHUNK=128 CTMR_MAP_WARPS=8
-CTMR_MAP_CHUNK=128 CTMR_MAP_WARPS=6
-CTMR_MAP_CHUNK=64
+CTMR_MAP_VARIANT=2
+CTMR_MAP_VARIANT=2 CTMR_MAP_ROLLED=0
 LIST
