@@ -15,8 +15,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libctmr.so")
-SOURCES = ["ctmr_kernels.cu", "ctmr_api.cu", "ctmr_synth_kernels.cu"]
-DEPS = SOURCES + ["ctmr_kernels.cuh", "ctmr_device.cuh", "ctmr_synth.h", "ctmr_synth_ecpoints.inc",
+SOURCES = ["ctmr_map.cu", "ctmr_map_alt.cu", "ctmr_reduce.cu", "ctmr_api.cu", "ctmr_synth_kernels.cu"]
+DEPS = SOURCES + ["ctmr_kernels.cuh", "ctmr_common.cuh", "ctmr_stream.cuh", "ctmr_device.cuh", "ctmr_synth.h",
+                  "ctmr_synth_ecpoints.inc",
                   os.path.join("..", "..", "include", "ctmr.h")]
 
 NVCC_FLAGS = [

@@ -101,7 +101,7 @@ __device__ __forceinline__ void sha256_compress(Sha256State& s, uint32_t (&w)[16
 // bank instead of immediates).  ~7 KB of code instead of ~26 KB: ncu charged 20 % of warp time to
 // "no_instruction" (instruction-cache misses) on the fully unrolled body once 8-16 desynchronised
 // warps per SM walk it at different offsets.
-__constant__ uint32_t kSha256K[64] = {
+static __constant__ uint32_t kSha256K[64] = {
     0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
     0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
     0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,

@@ -64,7 +64,7 @@ struct SmemWindow {
 // TLV header at `pos` inside [pos, lim): Go parseTagAndLength rules (single-octet tag, definite
 // minimal length, value inside the container).  Deliberately NOT inlined: the walker has ~30 call
 // sites and the map kernel's instruction footprint is what the SHA loop competes with for I-cache.
-__device__ __noinline__ uint64_t w_hdr_packed(SmemWindow rd, uint32_t pos, uint32_t lim) {
+static __device__ __noinline__ uint64_t w_hdr_packed(SmemWindow rd, uint32_t pos, uint32_t lim) {
     constexpr uint64_t kFail = ~0ull;
     if (pos + 2u > lim) return kFail;
     // the four bytes at `pos` in one go: two aligned 32-bit shared loads + a funnel shift
