@@ -351,6 +351,8 @@ def main():
     alg_bytes = total_bytes + wl["out_bytes"] * n  # sum(L_i) + 42*N (cfg2) / 54*N (cfg3-5), per launch
     achieved = alg_bytes / (map_ms / 1e3) / 1e9
     # N=1: 4 sub-batches x (len_order(3) + map(with insert) + resolve + pairs); N>1: + insert, partition(3), scatter
+    # measured INT-pipe ceiling of the fingerprint on this GPU: register-only SHA-256 at K_map's occupancy
+    int_ceiling_gbs = db.sha256_ceiling(iters=2000, rolled=True, ctas_per_sm=2)[0] if not args.no_fingerprint else None
     launches_per_step = 4 * 6 if world == 1 else NSUB * (4 + 3 + 4)
     map_launches = 4 if world == 1 else NSUB
     traffic, traffic_src = measured_traffic(n / map_launches)
@@ -424,6 +426,10 @@ def main():
                          "kernel_ms_per_step": map_ms, "kernel_ms": map_ms / map_launches,
                          "algorithmic_bytes_per_step": int(alg_bytes), "algorithmic_bytes_per_launch": int(alg_bytes / map_launches),
                          "launches_per_step": map_launches,
+                         "sha256_int_ceiling": None if int_ceiling_gbs is None else {
+                             "value": int_ceiling_gbs, "unit": "GB/s of message bytes",
+                             "how": "register-only SHA-256 microbenchmark (ctmr_sha256_ceiling_device), 16 warps/SM, run in this process",
+                             "k_map_frac": (total_bytes / (map_ms / 1e3) / 1e9) / int_ceiling_gbs},
                          "note": "SHA-256 is INT-pipe bound (DESIGN.md): see profiles/ for ALU-pipe utilisation; timed while the "
                                  "reduce kernels of the previous sub-batch share the GPU"},
             "gpu_launches": launches_per_step * K,

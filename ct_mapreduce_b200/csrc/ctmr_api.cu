@@ -855,6 +855,29 @@ int ctmr_snapshot_load(ctmr_ctx* c, const uint8_t* buf, uint64_t bytes) {
     return CTMR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ tooling
+int ctmr_sha256_ceiling_device(ctmr_ctx* c, uint32_t iters, uint32_t rolled, uint32_t ctas_per_sm, float* ms_out,
+                               uint64_t* blocks_out) {
+    if (!c || !iters || !ctas_per_sm || ctas_per_sm > 8) return fail(c, CTMR_E_INVALID, "bad argument");
+    CU(c, cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    CU(c, cudaEventCreate(&e0));
+    CU(c, cudaEventCreate(&e1));
+    uint32_t* sink = reinterpret_cast<uint32_t*>(c->small_dev + 90);
+    CU(c, launch_sha_ceiling(iters / 8 + 1, (int)rolled, (int)ctas_per_sm, c->sm_count, sink, c->stream));  // warm-up
+    CU(c, cudaEventRecord(e0, c->stream));
+    CU(c, launch_sha_ceiling(iters, (int)rolled, (int)ctas_per_sm, c->sm_count, sink, c->stream));
+    CU(c, cudaEventRecord(e1, c->stream));
+    CU(c, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(c, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
+    if (blocks_out) *blocks_out = (uint64_t)c->sm_count * ctas_per_sm * 256ull * iters;
+    return CTMR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ read side
 int ctmr_issuer_counts(ctmr_ctx* c, uint8_t* digests, uint64_t* counts, size_t* n) {
     if (!c || !n) return fail(c, CTMR_E_INVALID, "bad argument");

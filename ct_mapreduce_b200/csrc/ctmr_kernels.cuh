@@ -90,6 +90,7 @@ struct MapParams {
 cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_map_v1(const MapParams& p, int sm_count, cudaStream_t s);  // ctmr_map_alt.cu
 cudaError_t launch_map_v3(const MapParams& p, int sm_count, cudaStream_t s);  // ctmr_map_alt.cu
+cudaError_t launch_sha_ceiling(uint32_t iters, int rolled, int ctas_per_sm, int sm_count, uint32_t* sink, cudaStream_t s);
 cudaError_t launch_len_order(const uint64_t* offsets, uint64_t n, uint64_t blob_bytes, unsigned int* hist256, uint32_t* order,
                              cudaStream_t s);
 cudaError_t launch_insert(const DeviceState& st, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, cudaStream_t s);

@@ -426,6 +426,43 @@ cudaError_t launch_len_order(const uint64_t* offsets, uint64_t n, uint64_t blob_
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-only SHA-256 microbenchmark ("measure the INT ceiling ... rather than
+// trusting the estimate").  Same compression function as K_map, no memory traffic at all: every
+// lane chains `iters` compressions on register-resident message words.  Its rate is the practical
+// ceiling of the fingerprint on this part; bench.py --sha-ceiling reports it beside K_map's rate.
+// ------------------------------------------------------------------------------------------------
+template <int ROLLED>
+__global__ void __launch_bounds__(256) sha_ceiling_kernel(uint32_t iters, uint32_t one, uint32_t* __restrict__ sink) {
+    extern __shared__ uint8_t occupancy_pad[];  // only sized to pin the number of resident CTAs per SM
+    Sha256State st;
+    st.init();
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = (blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B9u + i;
+    for (uint32_t it = 0; it < iters; ++it) {
+        uint32_t m[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m[i] = w[i] ^ st.h[i & 7];  // data-dependent: nothing can be hoisted
+        if (ROLLED) sha256_compress_rolled(st, m, one);
+        else sha256_compress(st, m, one);
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc ^= st.h[i];
+    if (acc == 0x12345678u) sink[0] = acc;  // keeps the chain alive without a store per thread
+}
+
+cudaError_t launch_sha_ceiling(uint32_t iters, int rolled, int ctas_per_sm, int sm_count, uint32_t* sink, cudaStream_t s) {
+    // 256-thread CTAs; dynamic shared memory chosen so that exactly ctas_per_sm CTAs fit per SM
+    const int smem = ctas_per_sm >= 8 ? 0 : (int)((227 * 1024) / ctas_per_sm - 2048);
+    auto kern = rolled ? sha_ceiling_kernel<1> : sha_ceiling_kernel<0>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    kern<<<sm_count * ctas_per_sm, 256, smem, s>>>(iters, 1u, sink);
+    return cudaGetLastError();
+}
+
 // Shape of the persistent grid.  Defaults = the measured best (DESIGN.md "K_map tuning"); the
 // environment overrides exist for the A/B runs recorded under profiles/.
 cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {

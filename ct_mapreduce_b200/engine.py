@@ -187,6 +187,12 @@ class GpuCertDatabase:
         self._check(self._lib.ctmr_profile_last(self._h, C.byref(m), C.byref(t)))
         return m.value, t.value
 
+    def sha256_ceiling(self, iters=2000, rolled=True, ctas_per_sm=2):
+        """Register-only SHA-256 rate on this GPU: (GB/s of message bytes, ms)."""
+        ms, blocks = C.c_float(0), C.c_uint64(0)
+        self._check(self._lib.ctmr_sha256_ceiling_device(self._h, iters, int(rolled), ctas_per_sm, C.byref(ms), C.byref(blocks)))
+        return blocks.value * 64 / (ms.value / 1e3) / 1e9, ms.value
+
     def reset_device(self, stream=None):
         self._check(self._lib.ctmr_reset_device(self._h, stream))
 

@@ -240,6 +240,12 @@ int ctmr_reset_device(ctmr_ctx* ctx, void* stream);
 /* fails with CTMR_E_TABLE_FULL / CTMR_E_CUDA if any asynchronous launch since the last check failed */
 int ctmr_check_device(ctmr_ctx* ctx, void* stream);
 
+/* ---- measurement tooling -------------------------------------------------------------------- */
+/* Register-only SHA-256 microbenchmark: every lane chains `iters` compressions (K_map's own function, no
+ * memory traffic) at `ctas_per_sm` x 256 threads per SM.  The measured INT-pipe ceiling of the fingerprint. */
+int ctmr_sha256_ceiling_device(ctmr_ctx* ctx, uint32_t iters, uint32_t rolled, uint32_t ctas_per_sm, float* ms_out,
+                               uint64_t* blocks_out);
+
 /* ---- synthetic corpus on the device (bench/test tooling; ctmr_synth.h) ---------------------- */
 struct ctmr_synth_cfg;
 /* pass 1: offsets[0..n] (device) of entries [first, first+n); returns total bytes via *total_bytes */
