@@ -199,6 +199,10 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
     p.now_frac_nonzero = (ns - sec * 1000000000LL) != 0;
     p.one = 1;
     {
+        static const bool skip = getenv("CTMR_DEBUG_SKIP_WALK") && atoi(getenv("CTMR_DEBUG_SKIP_WALK"));
+        p.debug_skip_walk = skip;
+    }
+    {
         static const int sh[12] = {2, 13, 22, 6, 11, 25, 7, 18, 3, 17, 19, 10};
         for (int i = 0; i < 12; ++i) p.rot_mul[i] = 1u << (32 - sh[i]);
     }

@@ -60,7 +60,7 @@ struct MapParams {
     const uint32_t* issuer_idx;
     const uint32_t* issuer_map;
     uint32_t issuer_map_len;
-    uint32_t pad;
+    uint32_t debug_skip_walk;  // profiling aid (CTMR_DEBUG_SKIP_WALK=1): time K_map without the DER walker; results invalid
     uint64_t first_index;
     int64_t now_sec;
     uint32_t now_frac_nonzero;

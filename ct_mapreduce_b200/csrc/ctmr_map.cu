@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
             if (c < nch) {
                 const uint8_t* slot = my_slots + (size_t)s * 32 * Cfg::kSlot;
                 // ---- map: resume the TLV walk over the newly staged bytes
-                if (act && w.st < W_DONE) {
+                if (act && w.st < W_DONE && !p.debug_skip_walk) {
                     const uint32_t avail = min((c + 1u) * CHUNK, L);
                     const SmemWindow rd{(s ? slot1 : slot0) + m + OV - c * CHUNK};
                     walk_advance(w, rd, far, bad_span ? 0u : avail, L, p.filter, key_words);

@@ -21,9 +21,21 @@
 namespace ctmr {
 
 enum WalkState : uint32_t {
-    W_CERT = 0, W_TBS, W_VER, W_SERIAL, W_SIGALG, W_NAME, W_RDN, W_ATV, W_ATV_OID, W_ATV_VAL, W_VALIDITY, W_TIME1,
-    W_TIME2, W_SPKI, W_SPKI_ALG, W_SPKI_BITS, W_OPT1, W_OPT2, W_OPT3, W_EXTS, W_EXT, W_EXT_OID, W_EXT_CRIT, W_EXT_VAL,
-    W_BC_SEQ, W_BC_BOOL, W_BC_INT, W_SIGALG2, W_SIG, W_DONE, W_ERR
+    W_HEAD = 0,     // Certificate + TBSCertificate headers, optional [0] version
+    W_SERIAL,       // serialNumber (captured)
+    W_SIGALG,       // signature AlgorithmIdentifier (skipped)
+    W_NAME,         // issuer / subject Name header
+    W_NAMEWALK,     // SET OF { SEQ { OID, value } } ... loops inside the state
+    W_ATV_VAL_FAR,  // value header of an attribute whose OID was too long for one window (rare)
+    W_VALIDITY,     // both times in one step
+    W_SPKI,         // SubjectPublicKeyInfo: SEQ { AlgorithmIdentifier, BIT STRING }
+    W_SPKI_BITS,    // ... the BIT STRING header when the AlgorithmIdentifier was long (rare)
+    W_OPT,          // [1] issuerUniqueID, [2] subjectUniqueID, [3] extensions + their SEQUENCE header
+    W_EXTWALK,      // Extension ... loops inside the state, basicConstraints decoded inline
+    W_EXT_REST,     // critical / extnValue of an extension whose OID was too long for one window (rare)
+    W_TAIL,         // signatureAlgorithm + signatureValue headers
+    W_SIG,          // ... signatureValue header alone when the AlgorithmIdentifier was long (rare)
+    W_DONE, W_ERR
 };
 
 enum : uint32_t {
@@ -41,7 +53,7 @@ struct Walker {
     int64_t not_after;
 
     __device__ __forceinline__ void init() {
-        pos = 0; st = W_CERT; flags = 0; end_tbs = end_b = end_c = end_d = 0; which = 0;
+        pos = 0; st = W_HEAD; flags = 0; end_tbs = end_b = end_c = end_d = 0; which = 0;
         serial_off = serial_len = 0; not_after = 0;
         name_off = name_len = crldp_off = crldp_len = 0;
     }
@@ -181,41 +193,114 @@ __device__ __forceinline__ bool w_time(const R rd, uint32_t tag, uint32_t p, uin
     return true;
 }
 
+// basicConstraints ::= SEQUENCE { cA BOOLEAN DEFAULT FALSE, pathLenConstraint INTEGER OPTIONAL } filling
+// exactly the extnValue [vp, ve); "trailing data" and malformed members are errors (Go x509).
+template <class R>
+__device__ __forceinline__ bool w_basic_constraints(Walker& w, const R& rd, uint32_t vp, uint32_t ve) {
+    Tlv bc, f;
+    if (!w_hdr(rd, vp, ve, bc) || bc.tag != 0x30u || vp + bc.hdr + bc.len != ve) return false;
+    uint32_t bp = vp + bc.hdr;
+    bool ca = false;
+    if (bp < ve) {
+        if (!w_hdr(rd, bp, ve, f)) return false;
+        if (f.tag == 0x01u) {
+            if (f.len != 1u) return false;
+            const uint32_t bv = rd(bp + f.hdr);
+            if (bv != 0x00u && bv != 0xffu) return false;
+            ca = bv != 0u;
+            bp += f.hdr + f.len;
+            if (bp < ve && !w_hdr(rd, bp, ve, f)) return false;
+        }
+        if (bp < ve && (f.tag != 0x02u || f.len == 0u)) return false;
+    }
+    w.flags |= WF_BC_VALID;  // a later basicConstraints overrides an earlier one
+    w.flags = ca ? (w.flags | WF_IS_CA) : (w.flags & ~WF_IS_CA);
+    return true;
+}
+
+// critical BOOLEAN DEFAULT FALSE + extnValue OCTET STRING of the extension ending at `ee`, starting at `ip`
+template <class R>
+__device__ __forceinline__ bool w_ext_rest(Walker& w, const R& rd, uint32_t ip, uint32_t ee) {
+    Tlv v;
+    if (!w_hdr(rd, ip, ee, v)) return false;
+    if (v.tag == 0x01u) {
+        if (v.len != 1u) return false;
+        const uint32_t bv = rd(ip + v.hdr);
+        if (bv != 0x00u && bv != 0xffu) return false;
+        ip += v.hdr + v.len;
+        if (!w_hdr(rd, ip, ee, v)) return false;
+    }
+    if (v.tag != 0x04u) return false;
+    const uint32_t vp = ip + v.hdr;
+    if (w.which == 0x13u) return w_basic_constraints(w, rd, vp, vp + v.len);
+    if (w.which == 0x1fu) { w.crldp_off = vp; w.crldp_len = v.len; }  // cRLDistributionPoints
+    return true;
+}
+
+// Issuer.CommonName = the last 2.5.4.3 value of a string type; the issuerCNFilter prefixes are
+// evaluated right here, while the bytes are in shared memory (ct-fetch.go:57-63).
+template <class R, class F>
+__device__ __forceinline__ void w_note_cn(Walker& w, const R& rd, const F& far, uint32_t avail, uint32_t c0, uint32_t cnl,
+                                          const FilterCfg& flt) {
+    bool match = false;
+    for (uint32_t q = 0; q < flt.n_prefix && !match; ++q) {
+        const uint32_t po = flt.off[q], pl = flt.off[q + 1] - po;
+        if (pl > cnl) continue;
+        bool eq = true;
+        for (uint32_t i = 0; i < pl; ++i) {
+            const uint32_t x = c0 + i;
+            const uint32_t b = x < avail ? rd(x) : far(x);
+            if (b != flt.bytes[po + i]) { eq = false; break; }
+        }
+        match = eq;
+    }
+    w.flags |= WF_HAS_CN;
+    w.flags = match ? (w.flags | WF_CN_MATCH) : (w.flags & ~WF_CN_MATCH);
+}
+
 // Runs the walker as far as the staged bytes allow.
 //   rd(x)      byte x of the record from the shared-memory window (valid for x < avail)
 //   far(x)     byte x from global memory (only for a CommonName running past the window)
-//   avail      record bytes staged so far; avail == L means the whole record has been seen
+//   avail      record bytes staged so far; avail >= L means the whole record has been seen
 //   key_words  where the raw serial goes when it is met (10 words: len | serial[39], zero padded)
+// A state may loop over several TLVs; before every header it reads it makes sure kWalkNeed bytes from
+// `pos` are staged (or the record is complete) and otherwise returns with (st, pos, end_*) describing
+// exactly where to resume.  No single TLV step reads further than kWalkNeed bytes from its `pos`.
 template <class R, class F>
 __device__ inline void walk_advance(Walker& w, const R& rd, const F& far, uint32_t avail, uint32_t L,
                                     const FilterCfg& flt, uint32_t* __restrict__ key_words) {
     const bool final = avail >= L;
-    while (w.st < W_DONE) {
-        if (!final && w.pos + kWalkNeed > avail) return;  // suspend until the next chunk lands
-        Tlv t;
+#define W_NEED()                                              \
+    if (!final && w.pos + kWalkNeed > avail) return /* suspend until the next chunk lands */
+#define W_FAIL()         \
+    {                    \
+        w.st = W_ERR;    \
+        return;          \
+    }
+    Tlv t;
+    for (;;) {
         switch (w.st) {
-        case W_CERT:
-            if (!w_hdr(rd, 0, L, t) || t.tag != 0x30u || t.hdr + t.len != L) { w.st = W_ERR; break; }
-            w.pos = t.hdr;
-            w.st = W_TBS;
-            break;
-        case W_TBS:
-            if (!w_hdr(rd, w.pos, L, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
-            w.pos += t.hdr;
-            w.end_tbs = w.pos + t.len;
-            w.st = W_VER;
-            break;
-        case W_VER:  // [0] EXPLICIT version, optional
-            if (!w_hdr(rd, w.pos, w.end_tbs, t)) { w.st = W_ERR; break; }
-            if (t.tag == 0xa0u) w.pos += t.hdr + t.len;
+        case W_HEAD: {
+            W_NEED();
+            Tlv tbs;
+            if (!w_hdr(rd, 0, L, t) || t.tag != 0x30u || t.hdr + t.len != L) W_FAIL();
+            uint32_t p = t.hdr;
+            if (!w_hdr(rd, p, L, tbs) || tbs.tag != 0x30u) W_FAIL();
+            p += tbs.hdr;
+            w.end_tbs = p + tbs.len;
+            if (!w_hdr(rd, p, w.end_tbs, t)) W_FAIL();
+            if (t.tag == 0xa0u) p += t.hdr + t.len;  // [0] EXPLICIT version
+            w.pos = p;
             w.st = W_SERIAL;
             break;
+        }
         case W_SERIAL: {  // raw content octets, leading zeros kept (storage/types.go:171-178)
-            if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x02u || t.len == 0u) { w.st = W_ERR; break; }
+            W_NEED();
+            if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x02u || t.len == 0u) W_FAIL();
             const uint32_t c0 = w.pos + t.hdr;
             if (t.len > 1u) {
                 const uint32_t b0 = rd(c0), b1 = rd(c0 + 1);
-                if ((b0 == 0x00u && (b1 & 0x80u) == 0u) || (b0 == 0xffu && (b1 & 0x80u) != 0u)) { w.st = W_ERR; break; }
+                if ((b0 == 0x00u && (b1 & 0x80u) == 0u) || (b0 == 0xffu && (b1 & 0x80u) != 0u)) W_FAIL();
             }
             w.serial_off = c0;
             w.serial_len = t.len;
@@ -238,214 +323,187 @@ __device__ inline void walk_advance(Walker& w, const R& rd, const F& far, uint32
             break;
         }
         case W_SIGALG:
-            if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
+            W_NEED();
+            if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x30u) W_FAIL();
             w.pos += t.hdr + t.len;
             w.st = W_NAME;
             break;
         case W_NAME:  // issuer, then (WF_IN_SUBJECT) subject
-            if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
+            W_NEED();
+            if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x30u) W_FAIL();
             if (!(w.flags & WF_IN_SUBJECT)) { w.name_off = w.pos; w.name_len = t.hdr + t.len; }
             w.pos += t.hdr;
             w.end_b = w.pos + t.len;
-            w.st = w.pos < w.end_b ? W_RDN : ((w.flags & WF_IN_SUBJECT) ? W_SPKI : W_VALIDITY);
+            w.end_c = 0;  // no SET open
+            w.st = W_NAMEWALK;
             break;
-        case W_RDN:
-            if (!w_hdr(rd, w.pos, w.end_b, t) || t.tag != 0x31u) { w.st = W_ERR; break; }
-            w.pos += t.hdr;
-            w.end_c = w.pos + t.len;
-            if (w.pos < w.end_c) w.st = W_ATV;
-            else w.st = w.pos < w.end_b ? W_RDN : ((w.flags & WF_IN_SUBJECT) ? W_SPKI : W_VALIDITY);
-            break;
-        case W_ATV:
-            if (!w_hdr(rd, w.pos, w.end_c, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
-            w.pos += t.hdr;
-            w.end_d = w.pos + t.len;
-            w.st = W_ATV_OID;
-            break;
-        case W_ATV_OID: {
-            if (!w_hdr(rd, w.pos, w.end_d, t) || t.tag != 0x06u) { w.st = W_ERR; break; }
-            const uint32_t o = w.pos + t.hdr;
-            w.flags &= ~WF_IS_CN_OID;
-            if (!(w.flags & WF_IN_SUBJECT) && t.len == 3u && rd(o) == 0x55u && rd(o + 1) == 0x04u && rd(o + 2) == 0x03u)
-                w.flags |= WF_IS_CN_OID;
-            w.pos = o + t.len;
-            w.st = W_ATV_VAL;
-            break;
-        }
-        case W_ATV_VAL: {
-            if (!w_hdr(rd, w.pos, w.end_d, t)) { w.st = W_ERR; break; }
-            if ((w.flags & WF_IS_CN_OID) &&
-                (t.tag == 0x0cu || t.tag == 0x13u || t.tag == 0x16u || t.tag == 0x14u || t.tag == 0x12u)) {
-                // Issuer.CommonName = this value (the last one wins); evaluate the issuerCNFilter
-                // prefixes right now, while the bytes are in shared memory (ct-fetch.go:57-63)
-                const uint32_t c0 = w.pos + t.hdr, cnl = t.len;
-                bool match = false;
-                for (uint32_t q = 0; q < flt.n_prefix && !match; ++q) {
-                    const uint32_t po = flt.off[q], pl = flt.off[q + 1] - po;
-                    if (pl > cnl) continue;
-                    bool eq = true;
-                    for (uint32_t i = 0; i < pl; ++i) {
-                        const uint32_t x = c0 + i;
-                        const uint32_t b = x < avail ? rd(x) : far(x);
-                        if (b != flt.bytes[po + i]) { eq = false; break; }
-                    }
-                    match = eq;
+        case W_NAMEWALK:
+            for (;;) {
+                if (w.pos >= w.end_b) {
+                    w.st = (w.flags & WF_IN_SUBJECT) ? W_SPKI : W_VALIDITY;
+                    break;
                 }
-                w.flags |= WF_HAS_CN;
-                w.flags = match ? (w.flags | WF_CN_MATCH) : (w.flags & ~WF_CN_MATCH);
+                W_NEED();
+                if (w.pos >= w.end_c) {  // next RelativeDistinguishedName
+                    if (!w_hdr(rd, w.pos, w.end_b, t) || t.tag != 0x31u) W_FAIL();
+                    w.pos += t.hdr;
+                    w.end_c = w.pos + t.len;
+                    continue;
+                }
+                Tlv oid;
+                if (!w_hdr(rd, w.pos, w.end_c, t) || t.tag != 0x30u) W_FAIL();  // AttributeTypeAndValue
+                const uint32_t ap = w.pos + t.hdr, ae = ap + t.len;
+                if (!w_hdr(rd, ap, ae, oid) || oid.tag != 0x06u) W_FAIL();
+                const uint32_t o = ap + oid.hdr, vp = o + oid.len;
+                w.flags &= ~WF_IS_CN_OID;
+                if (!(w.flags & WF_IN_SUBJECT) && oid.len == 3u && rd(o) == 0x55u && rd(o + 1) == 0x04u && rd(o + 2) == 0x03u)
+                    w.flags |= WF_IS_CN_OID;
+                if (!final && vp + 6u > w.pos + kWalkNeed) {  // unusually long OID: value header in its own step
+                    w.end_d = ae;
+                    w.pos = vp;
+                    w.st = W_ATV_VAL_FAR;
+                    break;
+                }
+                Tlv val;
+                if (!w_hdr(rd, vp, ae, val)) W_FAIL();
+                if ((w.flags & WF_IS_CN_OID) &&
+                    (val.tag == 0x0cu || val.tag == 0x13u || val.tag == 0x16u || val.tag == 0x14u || val.tag == 0x12u))
+                    w_note_cn(w, rd, far, avail, vp + val.hdr, val.len, flt);
+                w.pos = ae;
             }
+            break;
+        case W_ATV_VAL_FAR:
+            W_NEED();
+            if (!w_hdr(rd, w.pos, w.end_d, t)) W_FAIL();
             w.pos = w.end_d;
-            if (w.pos < w.end_c) w.st = W_ATV;
-            else if (w.pos < w.end_b) w.st = W_RDN;
-            else w.st = (w.flags & WF_IN_SUBJECT) ? W_SPKI : W_VALIDITY;
+            w.st = W_NAMEWALK;
             break;
-        }
-        case W_VALIDITY:
-            if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
-            w.pos += t.hdr;
-            w.end_c = w.pos + t.len;
-            w.st = W_TIME1;
-            break;
-        case W_TIME1: {
+        case W_VALIDITY: {
+            W_NEED();
+            Tlv a, b;
             int64_t nb;
-            if (!w_hdr(rd, w.pos, w.end_c, t) || !w_time(rd, t.tag, w.pos + t.hdr, t.len, nb)) { w.st = W_ERR; break; }
-            w.pos += t.hdr + t.len;
-            w.st = W_TIME2;
-            break;
-        }
-        case W_TIME2:
-            if (!w_hdr(rd, w.pos, w.end_c, t) || !w_time(rd, t.tag, w.pos + t.hdr, t.len, w.not_after)) { w.st = W_ERR; break; }
-            w.pos = w.end_c;
+            if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x30u) W_FAIL();
+            uint32_t vp = w.pos + t.hdr;
+            const uint32_t ve = vp + t.len;
+            if (!w_hdr(rd, vp, ve, a) || !w_time(rd, a.tag, vp + a.hdr, a.len, nb)) W_FAIL();
+            vp += a.hdr + a.len;
+            if (!w_hdr(rd, vp, ve, b) || !w_time(rd, b.tag, vp + b.hdr, b.len, w.not_after)) W_FAIL();
+            w.pos = ve;
             w.flags |= WF_IN_SUBJECT;
             w.st = W_NAME;
             break;
-        case W_SPKI:
-            if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
-            w.pos += t.hdr;
-            w.end_c = w.pos + t.len;
-            w.st = W_SPKI_ALG;
-            break;
-        case W_SPKI_ALG:
-            if (!w_hdr(rd, w.pos, w.end_c, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
-            w.pos += t.hdr + t.len;
-            w.st = W_SPKI_BITS;
-            break;
-        case W_SPKI_BITS:
-            if (!w_hdr(rd, w.pos, w.end_c, t) || t.tag != 0x03u || t.len == 0u) { w.st = W_ERR; break; }
-            w.pos = w.end_c;
-            w.st = W_OPT1;
-            break;
-        case W_OPT1:  // [1] issuerUniqueID
-            if (w.pos >= w.end_tbs) { w.pos = w.end_tbs; w.st = W_SIGALG2; break; }
-            if (!w_hdr(rd, w.pos, w.end_tbs, t)) { w.st = W_ERR; break; }
-            if (t.tag == 0x81u || t.tag == 0xa1u) w.pos += t.hdr + t.len;
-            w.st = W_OPT2;
-            break;
-        case W_OPT2:  // [2] subjectUniqueID
-            if (w.pos >= w.end_tbs) { w.pos = w.end_tbs; w.st = W_SIGALG2; break; }
-            if (!w_hdr(rd, w.pos, w.end_tbs, t)) { w.st = W_ERR; break; }
-            if (t.tag == 0x82u || t.tag == 0xa2u) w.pos += t.hdr + t.len;
-            w.st = W_OPT3;
-            break;
-        case W_OPT3:  // [3] EXPLICIT extensions; anything else is tolerated trailing data
-            if (w.pos >= w.end_tbs) { w.pos = w.end_tbs; w.st = W_SIGALG2; break; }
-            if (!w_hdr(rd, w.pos, w.end_tbs, t)) { w.st = W_ERR; break; }
-            if (t.tag == 0xa3u) {
-                w.pos += t.hdr;
-                w.end_b = w.pos + t.len;
-                w.st = W_EXTS;
-            } else {
-                w.pos = w.end_tbs;
-                w.st = W_SIGALG2;
+        }
+        case W_SPKI: {
+            W_NEED();
+            Tlv a;
+            if (!w_hdr(rd, w.pos, w.end_tbs, t) || t.tag != 0x30u) W_FAIL();
+            const uint32_t kp = w.pos + t.hdr, ke = kp + t.len;
+            if (!w_hdr(rd, kp, ke, a) || a.tag != 0x30u) W_FAIL();
+            const uint32_t bp = kp + a.hdr + a.len;
+            w.end_c = ke;
+            w.which = 0;
+            if (!final && bp + 6u > w.pos + kWalkNeed) {  // long AlgorithmIdentifier (DSA / PSS parameters)
+                w.pos = bp;
+                w.st = W_SPKI_BITS;
+                break;
             }
-            break;
-        case W_EXTS:
-            if (!w_hdr(rd, w.pos, w.end_b, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
-            w.pos += t.hdr;
-            w.end_b = w.pos + t.len;
-            if (w.pos < w.end_b) w.st = W_EXT;
-            else { w.pos = w.end_tbs; w.st = W_SIGALG2; }
-            break;
-        case W_EXT:
-            if (!w_hdr(rd, w.pos, w.end_b, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
-            w.pos += t.hdr;
-            w.end_c = w.pos + t.len;
-            w.st = W_EXT_OID;
-            break;
-        case W_EXT_OID: {
-            if (!w_hdr(rd, w.pos, w.end_c, t) || t.tag != 0x06u) { w.st = W_ERR; break; }
-            const uint32_t o = w.pos + t.hdr;
-            w.which = (t.len == 3u && rd(o) == 0x55u && rd(o + 1) == 0x1du) ? rd(o + 2) : 0u;
-            w.pos = o + t.len;
-            w.st = W_EXT_CRIT;
+            if (!w_hdr(rd, bp, ke, t) || t.tag != 0x03u || t.len == 0u) W_FAIL();
+            w.pos = ke;
+            w.st = W_OPT;
             break;
         }
-        case W_EXT_CRIT:  // critical BOOLEAN DEFAULT FALSE
-            if (!w_hdr(rd, w.pos, w.end_c, t)) { w.st = W_ERR; break; }
-            if (t.tag == 0x01u) {
-                if (t.len != 1u) { w.st = W_ERR; break; }
-                const uint32_t bv = rd(w.pos + t.hdr);
-                if (bv != 0x00u && bv != 0xffu) { w.st = W_ERR; break; }
-                w.pos += t.hdr + t.len;
-            }
-            w.st = W_EXT_VAL;
-            break;
-        case W_EXT_VAL:
-            if (!w_hdr(rd, w.pos, w.end_c, t) || t.tag != 0x04u) { w.st = W_ERR; break; }
-            if (w.which == 0x13u) {  // basicConstraints: look inside the OCTET STRING
-                w.pos += t.hdr;
-                w.end_d = w.pos + t.len;
-                w.st = W_BC_SEQ;
-            } else {
-                if (w.which == 0x1fu) { w.crldp_off = w.pos + t.hdr; w.crldp_len = t.len; }  // cRLDistributionPoints
-                w.pos = w.end_c;
-                if (w.pos < w.end_b) w.st = W_EXT;
-                else { w.pos = w.end_tbs; w.st = W_SIGALG2; }
-            }
-            break;
-        case W_BC_SEQ:  // SEQ { cA BOOLEAN DEFAULT FALSE, pathLen INTEGER OPTIONAL }, no trailing data
-            if (!w_hdr(rd, w.pos, w.end_d, t) || t.tag != 0x30u || w.pos + t.hdr + t.len != w.end_d) { w.st = W_ERR; break; }
-            w.pos += t.hdr;
-            w.flags &= ~WF_BC_CA_TMP;
-            w.st = W_BC_BOOL;
-            break;
-        case W_BC_BOOL:
-            if (w.pos < w.end_d) {
-                if (!w_hdr(rd, w.pos, w.end_d, t)) { w.st = W_ERR; break; }
-                if (t.tag == 0x01u) {
-                    if (t.len != 1u) { w.st = W_ERR; break; }
-                    const uint32_t bv = rd(w.pos + t.hdr);
-                    if (bv != 0x00u && bv != 0xffu) { w.st = W_ERR; break; }
-                    if (bv) w.flags |= WF_BC_CA_TMP;
-                    w.pos += t.hdr + t.len;
-                }
-            }
-            w.st = W_BC_INT;
-            break;
-        case W_BC_INT:
-            if (w.pos < w.end_d) {
-                if (!w_hdr(rd, w.pos, w.end_d, t) || t.tag != 0x02u || t.len == 0u) { w.st = W_ERR; break; }
-            }
-            w.flags |= WF_BC_VALID;  // a later basicConstraints overrides an earlier one
-            w.flags = (w.flags & WF_BC_CA_TMP) ? (w.flags | WF_IS_CA) : (w.flags & ~WF_IS_CA);
+        case W_SPKI_BITS:
+            W_NEED();
+            if (!w_hdr(rd, w.pos, w.end_c, t) || t.tag != 0x03u || t.len == 0u) W_FAIL();
             w.pos = w.end_c;
-            if (w.pos < w.end_b) w.st = W_EXT;
-            else { w.pos = w.end_tbs; w.st = W_SIGALG2; }
+            w.which = 0;
+            w.st = W_OPT;
             break;
-        case W_SIGALG2:
-            if (!w_hdr(rd, w.pos, L, t) || t.tag != 0x30u) { w.st = W_ERR; break; }
-            w.pos += t.hdr + t.len;
-            w.st = W_SIG;
+        case W_OPT:  // which: 0 expecting [1] issuerUniqueID, 1 expecting [2] subjectUniqueID, 2 expecting [3] extensions
+            for (;;) {
+                if (w.pos >= w.end_tbs) {
+                    w.pos = w.end_tbs;
+                    w.st = W_TAIL;
+                    break;
+                }
+                W_NEED();
+                if (!w_hdr(rd, w.pos, w.end_tbs, t)) W_FAIL();
+                if (w.which == 0u) {
+                    w.which = 1;
+                    if (t.tag == 0x81u || t.tag == 0xa1u) { w.pos += t.hdr + t.len; continue; }
+                }
+                if (w.which == 1u) {
+                    w.which = 2;
+                    if (t.tag == 0x82u || t.tag == 0xa2u) { w.pos += t.hdr + t.len; continue; }
+                }
+                if (t.tag == 0xa3u) {  // [3] EXPLICIT Extensions ::= SEQUENCE OF Extension
+                    Tlv seq;
+                    const uint32_t xp = w.pos + t.hdr, xe = xp + t.len;
+                    if (!w_hdr(rd, xp, xe, seq) || seq.tag != 0x30u) W_FAIL();
+                    w.pos = xp + seq.hdr;
+                    w.end_b = w.pos + seq.len;
+                    w.st = W_EXTWALK;
+                } else {  // anything else is tolerated trailing data (encoding/asn1 struct parsing)
+                    w.pos = w.end_tbs;
+                    w.st = W_TAIL;
+                }
+                break;
+            }
             break;
-        case W_SIG:
-            if (!w_hdr(rd, w.pos, L, t) || t.tag != 0x03u || t.len == 0u) { w.st = W_ERR; break; }
+        case W_EXTWALK:
+            for (;;) {
+                if (w.pos >= w.end_b) {
+                    w.pos = w.end_tbs;
+                    w.st = W_TAIL;
+                    break;
+                }
+                W_NEED();
+                Tlv oid;
+                if (!w_hdr(rd, w.pos, w.end_b, t) || t.tag != 0x30u) W_FAIL();
+                const uint32_t ip = w.pos + t.hdr, ee = ip + t.len;
+                if (!w_hdr(rd, ip, ee, oid) || oid.tag != 0x06u) W_FAIL();
+                const uint32_t o = ip + oid.hdr, rest = o + oid.len;
+                w.which = (oid.len == 3u && rd(o) == 0x55u && rd(o + 1) == 0x1du) ? rd(o + 2) : 0u;
+                if (!final && rest + 24u > w.pos + kWalkNeed) {  // long OID: the remainder in its own step
+                    w.end_c = ee;
+                    w.pos = rest;
+                    w.st = W_EXT_REST;
+                    break;
+                }
+                if (!w_ext_rest(w, rd, rest, ee)) W_FAIL();
+                w.pos = ee;
+            }
+            break;
+        case W_EXT_REST:
+            W_NEED();
+            if (!w_ext_rest(w, rd, w.pos, w.end_c)) W_FAIL();
+            w.pos = w.end_c;
+            w.st = W_EXTWALK;
+            break;
+        case W_TAIL: {
+            W_NEED();
+            if (!w_hdr(rd, w.pos, L, t) || t.tag != 0x30u) W_FAIL();  // signatureAlgorithm
+            const uint32_t sp = w.pos + t.hdr + t.len;
+            if (!final && sp + 6u > w.pos + kWalkNeed) {
+                w.pos = sp;
+                w.st = W_SIG;
+                break;
+            }
+            if (!w_hdr(rd, sp, L, t) || t.tag != 0x03u || t.len == 0u) W_FAIL();  // signatureValue
             w.st = W_DONE;
-            break;
+            return;
+        }
+        case W_SIG:
+            W_NEED();
+            if (!w_hdr(rd, w.pos, L, t) || t.tag != 0x03u || t.len == 0u) W_FAIL();
+            w.st = W_DONE;
+            return;
         default:
-            w.st = W_ERR;
-            break;
+            return;  // W_DONE / W_ERR
         }
     }
+#undef W_NEED
+#undef W_FAIL
 }
 
 }  // namespace ctmr
