@@ -120,10 +120,18 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+#ifndef CTMR_SLOT_PAD
+#define CTMR_SLOT_PAD 16
+#endif
+
 template <int WARPS, int CHUNK, int LOADER, int ROLLED = 0>
 struct StreamCfg {
     static constexpr int kOverlap = 48;  // >= kWalkNeed, multiple of 16
-    static constexpr int kSlot = kOverlap + CHUNK + 16;
+    // Lane slots are kSlot bytes apart and every lane reads the same word of its own slot, so the stride
+    // decides the bank pattern: 16-byte granules (cp.async) allow at best 8 distinct bank groups; an odd
+    // number of granules per slot reaches that (4-way worst case), an even one collapses to 2 groups (16-way).
+    static constexpr int kSlotRaw = kOverlap + CHUNK + 16;
+    static constexpr int kSlot = kSlotRaw + (((kSlotRaw / 16) % 2 == 0) ? CTMR_SLOT_PAD : 0);
     static constexpr int kWarpBytes = 2 * 32 * kSlot;
     static constexpr int kBlocksPerChunk = CHUNK / 64;
     static constexpr int kPieces = kSlot / 16;
