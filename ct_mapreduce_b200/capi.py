@@ -29,6 +29,7 @@ EXPORTS = [
     "ctmr_process_device", "ctmr_partition_keys_device", "ctmr_scatter_bits_device", "ctmr_read_histogram_device",
     "ctmr_check_device", "ctmr_reset_device", "ctmr_profile_last", "ctmr_preload_known", "ctmr_snapshot_size",
     "ctmr_snapshot_save", "ctmr_snapshot_load", "ctmr_sha256_ceiling_device", "ctmr_synth_offsets_device", "ctmr_synth_write_device", "ctmr_synth_truth_device", "ctmr_synth_issuers_host",
+    "ctmr_process_raw", "ctmr_frontend_profile_last",  # include/ctmr_frontend.h
 ]
 
 
@@ -51,7 +52,7 @@ class DevBatch(C.Structure):
     _fields_ = [
         ("blob", C.c_void_p), ("blob_bytes", C.c_uint64), ("offsets", C.c_void_p), ("n", C.c_uint64),
         ("issuer_idx", C.c_void_p), ("issuer_map", C.c_void_p), ("issuer_map_len", C.c_uint32), ("reserved", C.c_uint32),
-        ("first_index", C.c_uint64), ("now_unix_ns", C.c_int64),
+        ("first_index", C.c_uint64), ("now_unix_ns", C.c_int64), ("lens", C.c_void_p),
     ]
 
 
@@ -59,6 +60,18 @@ class DevOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("status", "sha256", "exp_hour", "serial_off", "serial_len", "was_unknown", "first_issuer_hour", "keys",
                  "issuer_name_off", "issuer_name_len", "crldp_off", "crldp_len", "first_issuer_dn", "first_crldp")]
+
+
+class RawBatch(C.Structure):
+    """ctmr_raw_batch (include/ctmr_frontend.h)."""
+    _fields_ = [("text", C.c_void_p), ("text_bytes", C.c_uint64), ("leaf_input_off", C.c_void_p), ("leaf_input_len", C.c_void_p),
+                ("extra_data_off", C.c_void_p), ("extra_data_len", C.c_void_p), ("n", C.c_uint64), ("now_unix_ns", C.c_int64)]
+
+
+class RawOut(C.Structure):
+    """ctmr_raw_out (include/ctmr_frontend.h)."""
+    _fields_ = [("path", Out)] + [(n, C.c_void_p) for n in
+                                  ("entry_status", "entry_type", "timestamp_ms", "issuer", "leaf_src", "leaf_off", "leaf_len")]
 
 
 class SynthCfg(C.Structure):
@@ -132,6 +145,8 @@ def load():
     L.ctmr_synth_truth_device.argtypes = [C.POINTER(SynthCfg), u64, u64, vp, vp, vp, vp]
     L.ctmr_synth_issuers_host.argtypes = [C.POINTER(SynthCfg), vp, vp, u64]
     L.ctmr_synth_issuers_host.restype = u64
+    L.ctmr_process_raw.argtypes = [vp, C.POINTER(RawBatch), C.POINTER(RawOut)]
+    L.ctmr_frontend_profile_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
     for name in EXPORTS:
         getattr(L, name)  # every symbol include/ctmr.h declares must resolve
     _lib = L

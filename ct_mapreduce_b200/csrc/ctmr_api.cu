@@ -2,6 +2,7 @@
 // pipeline (H2D / kernels / D2H overlapped over three streams) and the device-resident entry points.
 // There is deliberately no CPU implementation of the path in this file or anywhere in the library:
 // without a CUDA device ctmr_create fails.
+#include <algorithm>
 #include <array>
 #include <cstdio>
 #include <cstdlib>
@@ -47,6 +48,40 @@ struct Stage {
     uint8_t* first_meta = nullptr;   // [2][E]: first_issuer_dn, first_crldp
 };
 
+// CT wire-format front end (include/ctmr_frontend.h): device buffers of one chunk + the device mirror of
+// the issuer registry keyed by certificate bytes
+struct FrontEnd {
+    uint64_t cap_entries = 0, cap_text = 0, cap_decoded = 0;
+    uint8_t* text = nullptr;  // [16 + cap_text + 64]
+    uint64_t *leaf_off = nullptr, *extra_off = nullptr, *pad_size = nullptr, *dec_off = nullptr;
+    uint32_t *leaf_len = nullptr, *extra_len = nullptr, *dec_len = nullptr;
+    uint8_t *str_bad = nullptr, *decoded = nullptr;
+    void* scan_temp = nullptr;
+    size_t scan_temp_bytes = 0;
+    uint8_t *entry_status = nullptr, *entry_type = nullptr, *leaf_src = nullptr;
+    uint64_t *timestamp = nullptr, *leaf_abs = nullptr, *chain_abs = nullptr, *tbs_abs = nullptr;
+    uint32_t *leaf_rel = nullptr, *leaf_len_out = nullptr, *chain_len = nullptr, *tbs_len = nullptr, *issuer_idx = nullptr;
+    // outputs of the path for this chunk
+    uint8_t *status = nullptr, *sha = nullptr, *was_unknown = nullptr, *first = nullptr, *first_meta = nullptr;
+    int64_t* exp_hour = nullptr;
+    uint32_t *serial_off = nullptr, *serial_len = nullptr, *spans = nullptr;
+    // issuer certificates by bytes
+    IssuerCertSlot* slots_dev = nullptr;
+    std::vector<IssuerCertSlot> slots_host;
+    uint64_t slot_mask = 0, slots_used = 0;
+    uint8_t* arena = nullptr;
+    uint64_t arena_cap = 0, arena_used = 0;
+    uint64_t* pending = nullptr;
+    uint64_t pending_mask = 0;
+    uint32_t* unknown_list = nullptr;
+    uint32_t unknown_cap = 0;
+    unsigned int* unknown_count = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    float fe_ms = 0.f, path_ms = 0.f;
+    uint64_t launches = 0;
+    std::vector<uint8_t> pack;  // host staging of the slow path (strings scattered over more than one chunk of text)
+};
+
 }  // namespace
 
 struct ctmr_ctx {
@@ -85,10 +120,15 @@ struct ctmr_ctx {
     int last_sub = 0;
     unsigned int* len_hist_sub[8] = {};
     unsigned long long* small_dev = nullptr;  // [64] cursors / cardinality result
+    FrontEnd* fe = nullptr;
     std::string err;
 };
 
 namespace {
+
+void fe_destroy(ctmr_ctx* c);
+int fe_add_issuer(ctmr_ctx* c, const std::string& der, uint32_t idx);
+int fe_clear_issuers(ctmr_ctx* c);
 
 int fail(ctmr_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -187,6 +227,7 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
     p.blob = b->blob;
     p.blob_bytes = b->blob_bytes;
     p.offsets = b->offsets;
+    p.lens = b->lens;
     p.n = b->n;
     p.issuer_idx = b->issuer_idx;
     p.issuer_map = b->issuer_map;
@@ -234,6 +275,147 @@ int reduce_on(ctmr_ctx* c, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, 
     if (!already_inserted) CU(c, launch_insert(c->st, keys, m, slot_of, s));
     CU(c, launch_resolve(c->st, keys, m, slot_of, pair_slot, was_unknown, s));
     CU(c, launch_resolve_pairs(c->st, keys, m, pair_slot, was_unknown, first, s));
+    return CTMR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ front end plumbing
+void fe_destroy(ctmr_ctx* c) {
+    FrontEnd* f = c->fe;
+    if (!f) return;
+    cudaFree(f->text); cudaFree(f->leaf_off); cudaFree(f->extra_off); cudaFree(f->pad_size); cudaFree(f->dec_off);
+    cudaFree(f->leaf_len); cudaFree(f->extra_len); cudaFree(f->dec_len); cudaFree(f->str_bad); cudaFree(f->decoded);
+    cudaFree(f->scan_temp); cudaFree(f->entry_status); cudaFree(f->entry_type); cudaFree(f->leaf_src); cudaFree(f->timestamp);
+    cudaFree(f->leaf_abs); cudaFree(f->chain_abs); cudaFree(f->tbs_abs); cudaFree(f->leaf_rel); cudaFree(f->leaf_len_out);
+    cudaFree(f->chain_len); cudaFree(f->tbs_len); cudaFree(f->issuer_idx); cudaFree(f->status); cudaFree(f->sha);
+    cudaFree(f->was_unknown); cudaFree(f->first); cudaFree(f->first_meta); cudaFree(f->exp_hour); cudaFree(f->serial_off);
+    cudaFree(f->serial_len); cudaFree(f->spans); cudaFree(f->slots_dev); cudaFree(f->arena); cudaFree(f->pending);
+    cudaFree(f->unknown_list); cudaFree(f->unknown_count);
+    if (f->ev0) cudaEventDestroy(f->ev0);
+    if (f->ev1) cudaEventDestroy(f->ev1);
+    if (f->ev2) cudaEventDestroy(f->ev2);
+    delete f;
+    c->fe = nullptr;
+}
+
+uint64_t host_issuer_cert_hash(const std::string& der) {
+    const uint32_t len = (uint32_t)der.size();
+    uint64_t acc = 0;
+    for (uint32_t i = 0; 8u * i < len; ++i) {
+        uint64_t w = 0;
+        const uint32_t rem = len - 8u * i;
+        std::memcpy(&w, der.data() + 8u * i, rem < 8u ? rem : 8u);  // little-endian host (x86-64 / aarch64)
+        acc += issuer_cert_word(w, i);
+    }
+    return issuer_cert_finish(acc, len);
+}
+
+// one more certificate in the device mirror: bytes into the arena, slot into the probe table
+int fe_add_issuer(ctmr_ctx* c, const std::string& der, uint32_t idx) {
+    FrontEnd* f = c->fe;
+    if (der.empty()) return CTMR_OK;  // the framing never yields an empty Chain[0]
+    if (2 * (f->slots_used + 1) > f->slot_mask + 1)
+        return fail(c, CTMR_E_TOO_MANY_ISSUERS, "more distinct Chain[0] certificates than the front end's table holds (raise config.max_issuers)");
+    const uint64_t padded = (der.size() + 15) & ~15ull;
+    if (f->arena_used + padded > f->arena_cap) {
+        uint64_t cap = f->arena_cap ? f->arena_cap * 2 : (64ull << 20);
+        while (f->arena_used + padded > cap) cap *= 2;
+        uint8_t* bigger = nullptr;
+        CU(c, cudaDeviceSynchronize());
+        CU(c, cudaMalloc(&bigger, cap));
+        if (f->arena_used) CU(c, cudaMemcpyAsync(bigger, f->arena, f->arena_used, cudaMemcpyDeviceToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(f->arena);
+        f->arena = bigger;
+        f->arena_cap = cap;
+    }
+    std::string buf = der;
+    buf.resize(padded, '\0');
+    CU(c, cudaMemcpyAsync(f->arena + f->arena_used, buf.data(), padded, cudaMemcpyHostToDevice, c->stream));
+    IssuerCertSlot sl{};
+    sl.h = host_issuer_cert_hash(der);
+    sl.len = (uint32_t)der.size();
+    sl.idx = idx;
+    sl.arena_off = f->arena_used;
+    f->arena_used += padded;
+    uint64_t slot = sl.h & f->slot_mask;
+    while (f->slots_host[slot].h != 0) slot = (slot + 1) & f->slot_mask;
+    f->slots_host[slot] = sl;
+    ++f->slots_used;
+    CU(c, cudaMemcpyAsync(f->slots_dev + slot, &sl, sizeof sl, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));  // both sources are locals
+    return CTMR_OK;
+}
+
+int fe_clear_issuers(ctmr_ctx* c) {
+    FrontEnd* f = c->fe;
+    CU(c, cudaDeviceSynchronize());
+    std::fill(f->slots_host.begin(), f->slots_host.end(), IssuerCertSlot{});
+    f->slots_used = 0;
+    f->arena_used = 0;
+    CU(c, cudaMemsetAsync(f->slots_dev, 0, (f->slot_mask + 1) * sizeof(IssuerCertSlot), c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CTMR_OK;
+}
+
+int ensure_frontend(ctmr_ctx* c) {
+    if (c->fe) return CTMR_OK;
+    FrontEnd* f = new (std::nothrow) FrontEnd();
+    if (!f) return fail(c, CTMR_E_NOMEM, "host allocation failed");
+    c->fe = f;
+    const uint64_t E = c->stage_entries;
+    uint64_t T = E * 6144ull < (64ull << 20) ? (64ull << 20) : E * 6144ull;  // leaf_input + extra_data characters per chunk
+    if (const char* ev = getenv("CTMR_FE_TEXT_CAP")) {  // tests shrink it to reach the multi-chunk and packing paths
+        const uint64_t v = strtoull(ev, nullptr, 10);
+        if (v >= (1ull << 16)) T = v;
+    }
+    f->cap_entries = E;
+    f->cap_text = T;
+    f->cap_decoded = T / 4 * 3 + 32 * E + 256;
+    auto bail = [&](int code) {
+        fe_destroy(c);
+        return code;
+    };
+#define FEM(ptr, bytes)                                                                    \
+    do {                                                                                   \
+        cudaError_t e_ = cudaMalloc(&(ptr), (bytes));                                      \
+        if (e_ != cudaSuccess) {                                                           \
+            fail(c, e_ == cudaErrorMemoryAllocation ? CTMR_E_NOMEM : CTMR_E_CUDA,           \
+                 std::string("front end: cudaMalloc: ") + cudaGetErrorString(e_));         \
+            return bail(e_ == cudaErrorMemoryAllocation ? CTMR_E_NOMEM : CTMR_E_CUDA);      \
+        }                                                                                  \
+    } while (0)
+    FEM(f->text, 16 + T + 64);
+    FEM(f->leaf_off, E * 8); FEM(f->extra_off, E * 8); FEM(f->leaf_len, E * 4); FEM(f->extra_len, E * 4);
+    FEM(f->pad_size, (2 * E + 1) * 8); FEM(f->dec_off, (2 * E + 1) * 8); FEM(f->dec_len, 2 * E * 4); FEM(f->str_bad, 2 * E);
+    FEM(f->decoded, f->cap_decoded);
+    f->scan_temp_bytes = fe_scan_temp_bytes(2 * E + 1);
+    FEM(f->scan_temp, f->scan_temp_bytes ? f->scan_temp_bytes : 16);
+    FEM(f->entry_status, E); FEM(f->entry_type, E); FEM(f->leaf_src, E); FEM(f->timestamp, E * 8);
+    FEM(f->leaf_abs, E * 8); FEM(f->chain_abs, E * 8); FEM(f->tbs_abs, E * 8);
+    FEM(f->leaf_rel, E * 4); FEM(f->leaf_len_out, E * 4); FEM(f->chain_len, E * 4); FEM(f->tbs_len, E * 4); FEM(f->issuer_idx, E * 4);
+    FEM(f->status, E); FEM(f->sha, E * 32); FEM(f->was_unknown, E); FEM(f->first, E); FEM(f->first_meta, 2 * E);
+    FEM(f->exp_hour, E * 8); FEM(f->serial_off, E * 4); FEM(f->serial_len, E * 4); FEM(f->spans, 4 * E * 4);
+    f->slot_mask = pow2_at_least(4ull * c->st.max_issuers) - 1;
+    FEM(f->slots_dev, (f->slot_mask + 1) * sizeof(IssuerCertSlot));
+    f->slots_host.assign(f->slot_mask + 1, IssuerCertSlot{});
+    f->pending_mask = (1ull << 16) - 1;
+    FEM(f->pending, (f->pending_mask + 1) * 8);
+    f->unknown_cap = 1u << 14;
+    FEM(f->unknown_list, f->unknown_cap * 4);
+    FEM(f->unknown_count, 16);
+#undef FEM
+    if (cudaMemsetAsync(f->slots_dev, 0, (f->slot_mask + 1) * sizeof(IssuerCertSlot), c->stream) != cudaSuccess ||
+        cudaMemsetAsync(f->text, 0, 16 + T + 64, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
+        cudaEventCreate(&f->ev0) != cudaSuccess ||
+        cudaEventCreate(&f->ev1) != cudaSuccess || cudaEventCreate(&f->ev2) != cudaSuccess) {
+        fail(c, CTMR_E_CUDA, "front end: initialisation failed");
+        return bail(CTMR_E_CUDA);
+    }
+    for (const auto& kv : c->issuer_by_der) {  // certificates registered before the front end existed
+        int rc = fe_add_issuer(c, kv.first, kv.second);
+        if (rc) return rc;
+    }
     return CTMR_OK;
 }
 
@@ -355,6 +537,7 @@ void ctmr_destroy(ctmr_ctx* c) {
     if (c->stream_a) cudaStreamDestroy(c->stream_a);
     if (c->stream_b) cudaStreamDestroy(c->stream_b);
     if (c->stream) cudaStreamDestroy(c->stream);
+    fe_destroy(c);
     delete c;
 }
 
@@ -419,6 +602,10 @@ int ctmr_register_issuers(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offs
                 }
             }
             c->issuer_by_der.emplace(ders[fresh[i]], idx);
+            if (c->fe) {
+                int rc2 = fe_add_issuer(c, ders[fresh[i]], idx);
+                if (rc2) return rc2;
+            }
         }
         for (uint32_t k = 0; k < n; ++k)
             if (dense_out[k] == CTMR_ISSUER_NONE) dense_out[k] = c->issuer_by_der[ders[k]];
@@ -452,7 +639,7 @@ int ctmr_map_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o,
             c->order_cap = b->n;
         }
         if (!c->len_hist) CU(c, cudaMalloc(&c->len_hist, 256 * sizeof(unsigned int)));
-        CU(c, launch_len_order(b->offsets, b->n, b->blob_bytes, c->len_hist, c->order_scratch, s));
+        CU(c, launch_len_order(b->offsets, b->lens, b->n, b->blob_bytes, c->len_hist, c->order_scratch, s));
         p.order = c->order_scratch;
     }
     CU(c, launch_map(p, c->sm_count, s));
@@ -513,6 +700,7 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
         const uint64_t lo = b->n * k / nsub, hi = b->n * (k + 1) / nsub, cnt = hi - lo;
         ctmr_dev_batch sb = *b;
         sb.offsets = b->offsets + lo;
+        sb.lens = b->lens ? b->lens + lo : nullptr;
         sb.n = cnt;
         sb.issuer_idx = b->issuer_idx ? b->issuer_idx + lo : nullptr;
         sb.first_index = b->first_index + lo;
@@ -531,7 +719,7 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
         fill_map_params(c, &sb, &so, p, 3, c->fuse_insert ? c->slot_scratch + lo : nullptr);
         CU(c, cudaEventRecord(c->ev_map0[k], c->stream_a));
         if (c->bucket_by_length && cnt > 64 && p.sha256) {
-            CU(c, launch_len_order(sb.offsets, cnt, sb.blob_bytes, c->len_hist_sub[k], c->order_scratch + lo, c->stream_a));
+            CU(c, launch_len_order(sb.offsets, sb.lens, cnt, sb.blob_bytes, c->len_hist_sub[k], c->order_scratch + lo, c->stream_a));
             p.order = c->order_scratch + lo;
         }
         CU(c, launch_map(p, c->sm_count, c->stream_a));
@@ -700,7 +888,7 @@ int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets
         MapParams p;
         fill_map_params(c, &db, &dout, p, sub % kStages, c->fuse_insert ? s.slot_of : nullptr);
         if (c->bucket_by_length && cnt > 64 && p.sha256) {
-            CU(c, launch_len_order(s.offsets, cnt, db.blob_bytes, s.len_hist, s.order, s.stream));
+            CU(c, launch_len_order(s.offsets, nullptr, cnt, db.blob_bytes, s.len_hist, s.order, s.stream));
             p.order = s.order;
         }
         CU(c, launch_map(p, c->sm_count, s.stream));
@@ -848,6 +1036,7 @@ int ctmr_snapshot_load(ctmr_ctx* c, const uint8_t* buf, uint64_t bytes) {
     c->digests.clear();
     c->issuer_by_digest.clear();
     c->issuer_by_der.clear();  // DER memo is rebuilt lazily; dense indices come from the digests
+    if (c->fe) fe_clear_issuers(c);
     for (uint64_t i = 0; i < h.n_issuers; ++i) {
         std::array<uint8_t, 32> a;
         std::memcpy(a.data(), p, 32);
@@ -933,6 +1122,196 @@ int ctmr_table_stats(ctmr_ctx* c, uint64_t* used, uint64_t* capacity) {
     CU(c, cudaStreamSynchronize(c->stream));
     if (used) *used = u;
     if (capacity) *capacity = c->st.table_mask + 1;
+    return CTMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ CT wire-format front end
+// get-entries strings -> decode -> framing -> Chain[0] identification -> the path.
+int ctmr_process_raw(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {
+    if (!c || !b || !out) return fail(c, CTMR_E_INVALID, "bad argument");
+    if (b->n && (!b->text || !b->leaf_input_off || !b->leaf_input_len || !b->extra_data_off || !b->extra_data_len))
+        return fail(c, CTMR_E_INVALID, "null batch buffers");
+    if (b->n == 0) return CTMR_OK;
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_frontend(c);
+    if (rc) return rc;
+    FrontEnd* f = c->fe;
+    f->fe_ms = f->path_ms = 0.f;
+    f->launches = 0;
+    cudaStream_t s = c->stream;
+    const ctmr_out* po = &out->path;
+    const bool want_meta = po->first_issuer_dn || po->first_crldp || po->issuer_name_off || po->crldp_off;
+    const uint64_t E = f->cap_entries;
+    std::vector<uint64_t> lo_off, ex_off;  // chunk-relative string offsets
+    uint64_t lo = 0;
+    while (lo < b->n) {
+        // ---- chunk = as many entries as fit the entry and character budgets
+        uint64_t hi = lo, chars = 0, min_off = ~0ull, max_end = 0;
+        while (hi < b->n && hi - lo < E) {
+            const uint64_t l0 = b->leaf_input_off[hi], l1 = l0 + b->leaf_input_len[hi];
+            const uint64_t x0 = b->extra_data_off[hi], x1 = x0 + b->extra_data_len[hi];
+            if (l1 > b->text_bytes || x1 > b->text_bytes) return fail(c, CTMR_E_INVALID, "string span outside the text buffer");
+            const uint64_t add = (uint64_t)b->leaf_input_len[hi] + b->extra_data_len[hi];
+            if (chars + add > f->cap_text / 2) break;
+            chars += add;
+            min_off = std::min(min_off, std::min(l0, x0));
+            max_end = std::max(max_end, std::max(l1, x1));
+            ++hi;
+        }
+        if (hi == lo) return fail(c, CTMR_E_BATCH_TOO_LARGE, "a single entry exceeds the front end's character budget");
+        const uint64_t cnt = hi - lo;
+        lo_off.resize(cnt);
+        ex_off.resize(cnt);
+        uint64_t text_bytes = 0;
+        if (max_end - min_off <= f->cap_text) {  // strings in place inside the response bodies: one copy
+            text_bytes = max_end - min_off;
+            for (uint64_t i = 0; i < cnt; ++i) {
+                lo_off[i] = b->leaf_input_off[lo + i] - min_off;
+                ex_off[i] = b->extra_data_off[lo + i] - min_off;
+            }
+            CU(c, cudaMemcpyAsync(f->text + 16, b->text + min_off, text_bytes, cudaMemcpyHostToDevice, s));
+        } else {  // scattered: pack on the host first
+            f->pack.resize(chars);
+            uint64_t w = 0;
+            for (uint64_t i = 0; i < cnt; ++i) {
+                lo_off[i] = w;
+                std::memcpy(f->pack.data() + w, b->text + b->leaf_input_off[lo + i], b->leaf_input_len[lo + i]);
+                w += b->leaf_input_len[lo + i];
+                ex_off[i] = w;
+                std::memcpy(f->pack.data() + w, b->text + b->extra_data_off[lo + i], b->extra_data_len[lo + i]);
+                w += b->extra_data_len[lo + i];
+            }
+            text_bytes = w;
+            CU(c, cudaMemcpyAsync(f->text + 16, f->pack.data(), text_bytes, cudaMemcpyHostToDevice, s));
+        }
+        CU(c, cudaMemcpyAsync(f->leaf_off, lo_off.data(), cnt * 8, cudaMemcpyHostToDevice, s));
+        CU(c, cudaMemcpyAsync(f->extra_off, ex_off.data(), cnt * 8, cudaMemcpyHostToDevice, s));
+        CU(c, cudaMemcpyAsync(f->leaf_len, b->leaf_input_len + lo, cnt * 4, cudaMemcpyHostToDevice, s));
+        CU(c, cudaMemcpyAsync(f->extra_len, b->extra_data_len + lo, cnt * 4, cudaMemcpyHostToDevice, s));
+        FeParams p{};
+        p.text = f->text + 16;
+        p.text_bytes = text_bytes;
+        p.leaf_off = f->leaf_off; p.leaf_len = f->leaf_len; p.extra_off = f->extra_off; p.extra_len = f->extra_len;
+        p.n = cnt;
+        p.pad_size = f->pad_size; p.dec_off = f->dec_off; p.dec_len = f->dec_len; p.str_bad = f->str_bad; p.decoded = f->decoded;
+        p.entry_status = f->entry_status; p.entry_type = f->entry_type; p.timestamp = f->timestamp; p.leaf_src = f->leaf_src;
+        p.leaf_rel = f->leaf_rel; p.leaf_len_out = f->leaf_len_out; p.leaf_abs = f->leaf_abs; p.chain_abs = f->chain_abs;
+        p.chain_len = f->chain_len; p.tbs_abs = f->tbs_abs; p.tbs_len = f->tbs_len; p.issuer_idx = f->issuer_idx;
+        CU(c, cudaEventRecord(f->ev0, s));
+        CU(c, launch_fe_decode(p, f->scan_temp, f->scan_temp_bytes, c->sm_count, s));
+        CU(c, launch_fe_frame(p, s));
+        f->launches += 5;  // sizes, scan (cub: one kernel visible to us), decode, frame, tbs
+        // ---- Chain[0] -> dense index; certificates never seen before go through ctmr_register_issuers once
+        for (int round = 0;; ++round) {
+            if (round > 64) return fail(c, CTMR_E_CUDA, "front end: issuer identification does not converge");
+            IssuerCertTable tab{f->slots_dev, f->slot_mask, f->arena};
+            CU(c, cudaMemsetAsync(f->pending, 0, (f->pending_mask + 1) * 8, s));
+            CU(c, cudaMemsetAsync(f->unknown_count, 0, 4, s));
+            CU(c, launch_fe_issuer(p, tab, f->pending, f->pending_mask, f->unknown_list, f->unknown_cap, f->unknown_count, c->sm_count, s));
+            ++f->launches;
+            unsigned int n_unknown = 0;
+            CU(c, cudaMemcpyAsync(&n_unknown, f->unknown_count, 4, cudaMemcpyDeviceToHost, s));
+            CU(c, cudaStreamSynchronize(s));
+            if (n_unknown == 0) break;
+            if (n_unknown > f->unknown_cap) n_unknown = f->unknown_cap;  // the rest shows up again next round
+            std::vector<uint32_t> list(n_unknown);
+            CU(c, cudaMemcpyAsync(list.data(), f->unknown_list, n_unknown * 4ull, cudaMemcpyDeviceToHost, s));
+            CU(c, cudaStreamSynchronize(s));
+            std::vector<uint8_t> blob;
+            std::vector<uint64_t> offs(1, 0);
+            for (uint32_t e : list) {
+                uint64_t at = 0;
+                uint32_t len = 0;
+                CU(c, cudaMemcpyAsync(&at, f->chain_abs + e, 8, cudaMemcpyDeviceToHost, s));
+                CU(c, cudaMemcpyAsync(&len, f->chain_len + e, 4, cudaMemcpyDeviceToHost, s));
+                CU(c, cudaStreamSynchronize(s));
+                const size_t w = blob.size();
+                blob.resize(w + len);
+                CU(c, cudaMemcpyAsync(blob.data() + w, f->decoded + at, len, cudaMemcpyDeviceToHost, s));
+                CU(c, cudaStreamSynchronize(s));
+                offs.push_back(blob.size());
+            }
+            std::vector<uint32_t> dense(n_unknown);
+            const uint64_t before = f->slots_used;
+            rc = ctmr_register_issuers(c, blob.data(), offs.data(), n_unknown, dense.data());
+            if (rc) return rc;
+            if (f->slots_used == before) return fail(c, CTMR_E_CUDA, "front end: unresolved Chain[0] is already registered");
+        }
+        CU(c, cudaEventRecord(f->ev1, s));
+        // ---- the path over the decoded arena: leaves stay where the decoder put them
+        ctmr_dev_batch db{};
+        db.blob = f->decoded;
+        CU(c, cudaMemcpyAsync(&db.blob_bytes, f->dec_off + 2 * cnt, 8, cudaMemcpyDeviceToHost, s));
+        CU(c, cudaStreamSynchronize(s));
+        db.offsets = f->leaf_abs;
+        db.lens = f->leaf_len_out;
+        db.n = cnt;
+        db.issuer_idx = f->issuer_idx;
+        db.first_index = c->next_index + lo;
+        db.now_unix_ns = b->now_unix_ns;
+        ctmr_dev_out dout{};
+        dout.status = f->status;
+        dout.sha256 = po->sha256 ? f->sha : nullptr;
+        dout.exp_hour = f->exp_hour;
+        dout.serial_off = f->serial_off;
+        dout.serial_len = f->serial_len;
+        dout.was_unknown = f->was_unknown;
+        dout.first_issuer_hour = f->first;
+        if (want_meta) {
+            dout.issuer_name_off = f->spans;
+            dout.issuer_name_len = f->spans + E;
+            dout.crldp_off = f->spans + 2 * E;
+            dout.crldp_len = f->spans + 3 * E;
+            dout.first_issuer_dn = f->first_meta;
+            dout.first_crldp = f->first_meta + E;
+        }
+        rc = ctmr_process_device(c, &db, &dout, s);
+        if (rc) return rc;
+        CU(c, launch_fe_finish(p, f->status, s));
+        ++f->launches;
+        CU(c, cudaEventRecord(f->ev2, s));
+#define FE_D2H(dst, src, bytes) \
+    if (dst) CU(c, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(dst) + lo * ((bytes) / cnt), (src), (bytes), cudaMemcpyDeviceToHost, s))
+        FE_D2H(po->status, f->status, cnt);
+        FE_D2H(po->sha256, f->sha, cnt * 32);
+        FE_D2H(po->exp_hour, f->exp_hour, cnt * 8);
+        FE_D2H(po->serial_off, f->serial_off, cnt * 4);
+        FE_D2H(po->serial_len, f->serial_len, cnt * 4);
+        FE_D2H(po->was_unknown, f->was_unknown, cnt);
+        FE_D2H(po->first_issuer_hour, f->first, cnt);
+        if (want_meta) {
+            FE_D2H(po->issuer_name_off, dout.issuer_name_off, cnt * 4);
+            FE_D2H(po->issuer_name_len, dout.issuer_name_len, cnt * 4);
+            FE_D2H(po->crldp_off, dout.crldp_off, cnt * 4);
+            FE_D2H(po->crldp_len, dout.crldp_len, cnt * 4);
+            FE_D2H(po->first_issuer_dn, dout.first_issuer_dn, cnt);
+            FE_D2H(po->first_crldp, dout.first_crldp, cnt);
+        }
+        FE_D2H(out->entry_status, f->entry_status, cnt);
+        FE_D2H(out->entry_type, f->entry_type, cnt);
+        FE_D2H(out->timestamp_ms, f->timestamp, cnt * 8);
+        FE_D2H(out->issuer, f->issuer_idx, cnt * 4);
+        FE_D2H(out->leaf_src, f->leaf_src, cnt);
+        FE_D2H(out->leaf_off, f->leaf_rel, cnt * 4);
+        FE_D2H(out->leaf_len, f->leaf_len_out, cnt * 4);
+#undef FE_D2H
+        CU(c, cudaStreamSynchronize(s));
+        float a = 0.f, d = 0.f;
+        CU(c, cudaEventElapsedTime(&a, f->ev0, f->ev1));
+        CU(c, cudaEventElapsedTime(&d, f->ev1, f->ev2));
+        f->fe_ms += a;
+        f->path_ms += d;
+        lo = hi;
+    }
+    c->next_index += b->n;
+    return ctmr_check_device(c, nullptr);
+}
+
+int ctmr_frontend_profile_last(ctmr_ctx* c, float* frontend_ms, float* path_ms, uint64_t* frontend_launches) {
+    if (!c || !c->fe) return fail(c, CTMR_E_INVALID, "no ctmr_process_raw call to report");
+    if (frontend_ms) *frontend_ms = c->fe->fe_ms;
+    if (path_ms) *path_ms = c->fe->path_ms;
+    if (frontend_launches) *frontend_launches = c->fe->launches;
     return CTMR_OK;
 }
 

@@ -391,15 +391,14 @@ __device__ inline bool der_name(const uint8_t* __restrict__ d, uint32_t pos, uin
 
 // Certificate ::= SEQ { TBS, sigAlg, BIT STRING }.  Returns false on anything a strict reading of
 // RFC 5280 rejects in the fields the path uses; never reads outside [d, d+len).
-__device__ inline bool parse_cert(const uint8_t* __restrict__ d, uint32_t len, ParsedCert& pc) {
+// TBSCertificate at d[pos..len): everything the path reads from it.  tbs_end = offset just past it.
+__device__ inline bool parse_tbs(const uint8_t* __restrict__ d, uint32_t pos, uint32_t len, ParsedCert& pc, uint32_t& tbs_end) {
     pc.serial_off = pc.serial_len = pc.cn_off = pc.cn_len = 0;
     pc.spki_off = pc.spki_len = pc.crldp_off = pc.crldp_len = 0;
     pc.issuer_off = pc.issuer_len = 0;
     pc.not_after = 0;
     pc.flags = 0;
-    Tlv cert, tbs, t;
-    if (!der_read(d, 0, len, cert) || cert.tag != 0x30u || cert.hdr + cert.len != len) return false;
-    uint32_t pos = cert.hdr;
+    Tlv tbs, t;
     if (!der_read(d, pos, len, tbs) || tbs.tag != 0x30u) return false;
     uint32_t tp = pos + tbs.hdr, tend = tp + tbs.len;
     if (!der_read(d, tp, tend, t)) return false;
@@ -508,7 +507,15 @@ __device__ inline bool parse_cert(const uint8_t* __restrict__ d, uint32_t len, P
             ep += ext.hdr + ext.len;
         }
     }
-    pos += tbs.hdr + tbs.len;
+    tbs_end = pos + tbs.hdr + tbs.len;
+    return true;
+}
+
+__device__ inline bool parse_cert(const uint8_t* __restrict__ d, uint32_t len, ParsedCert& pc) {
+    Tlv cert, t;
+    if (!der_read(d, 0, len, cert) || cert.tag != 0x30u || cert.hdr + cert.len != len) return false;
+    uint32_t pos = cert.hdr;
+    if (!parse_tbs(d, pos, len, pc, pos)) return false;
     if (!der_read(d, pos, len, t) || t.tag != 0x30u) return false;  // signatureAlgorithm
     pos += t.hdr + t.len;
     if (!der_read(d, pos, len, t) || t.tag != 0x03u || t.len == 0u) return false;  // signatureValue

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "../../include/ctmr.h"
+#include "../../include/ctmr_frontend.h"
 
 namespace ctmr {
 
@@ -56,6 +57,7 @@ struct MapParams {
     const uint8_t* blob;
     uint64_t blob_bytes;
     const uint64_t* offsets;
+    const uint32_t* lens;  // optional explicit lengths (records not contiguous)
     uint64_t n;
     const uint32_t* issuer_idx;
     const uint32_t* issuer_map;
@@ -91,7 +93,7 @@ cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_map_v1(const MapParams& p, int sm_count, cudaStream_t s);  // ctmr_map_alt.cu
 cudaError_t launch_map_v3(const MapParams& p, int sm_count, cudaStream_t s);  // ctmr_map_alt.cu
 cudaError_t launch_sha_ceiling(uint32_t iters, int rolled, int ctas_per_sm, int sm_count, uint32_t* sink, cudaStream_t s);
-cudaError_t launch_len_order(const uint64_t* offsets, uint64_t n, uint64_t blob_bytes, unsigned int* hist256, uint32_t* order,
+cudaError_t launch_len_order(const uint64_t* offsets, const uint32_t* lens, uint64_t n, uint64_t blob_bytes, unsigned int* hist256, uint32_t* order,
                              cudaStream_t s);
 cudaError_t launch_insert(const DeviceState& st, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, cudaStream_t s);
 cudaError_t launch_resolve(const DeviceState& st, const ctmr_key* keys, uint64_t m, const uint32_t* slot_of,
@@ -112,5 +114,73 @@ cudaError_t launch_partition(const ctmr_key* keys, uint64_t n, uint32_t world, c
                              cudaStream_t s);
 cudaError_t launch_scatter_bits(const uint8_t* a, const uint8_t* b, const uint32_t* src_pos, uint64_t m, uint8_t* a_dst,
                                 uint8_t* b_dst, cudaStream_t s);
+
+// ---- CT wire-format front end (ctmr_frontend.cu, include/ctmr_frontend.h) ------------------------
+#define CTMR_ISSUER_UNRESOLVED 0xFFFFFFFDu  // internal: Chain[0] present, dense index not looked up yet
+
+struct FeParams {
+    const uint8_t* text;        // device copy of the batch's characters (slack of 16 bytes on both sides)
+    uint64_t text_bytes;
+    const uint64_t* leaf_off;   // [n] string spans inside text
+    const uint32_t* leaf_len;
+    const uint64_t* extra_off;
+    const uint32_t* extra_len;
+    uint64_t n;
+    // string s = 2*entry + (0: leaf_input, 1: extra_data)
+    uint64_t* pad_size;         // [2n+1] decoded size rounded up to 16
+    uint64_t* dec_off;          // [2n+1] placement in the decoded arena (exclusive scan of pad_size)
+    uint32_t* dec_len;          // [2n]
+    uint8_t* str_bad;           // [2n]
+    uint8_t* decoded;           // arena
+    // per entry
+    uint8_t* entry_status;
+    uint8_t* entry_type;
+    uint64_t* timestamp;
+    uint8_t* leaf_src;
+    uint32_t* leaf_rel;
+    uint32_t* leaf_len_out;
+    uint64_t* leaf_abs;         // arena offset of the certificate K_map processes
+    uint64_t* chain_abs;        // arena offset / length of Chain[0]
+    uint32_t* chain_len;
+    uint64_t* tbs_abs;          // precert entries: the leaf's TBSCertificate
+    uint32_t* tbs_len;
+    uint32_t* issuer_idx;
+};
+
+// Device mirror of the issuer registry keyed by the certificate BYTES: Chain[0] repeats for millions of
+// entries, so it is hashed, probed and compared in full on the GPU and parsed once per distinct value.
+struct IssuerCertSlot {
+    uint64_t h;          // 0 = empty
+    uint32_t len;
+    uint32_t idx;        // dense issuer index or CTMR_ISSUER_BAD
+    uint64_t arena_off;  // 16-byte aligned, zero padded to a multiple of 16
+    uint64_t pad;
+};
+struct IssuerCertTable {
+    const IssuerCertSlot* slots;
+    uint64_t mask;
+    const uint8_t* arena;
+};
+
+// hash of a byte string = finish(sum over its little-endian 8-byte words (zero padded) of word(w, i), length):
+// a commutative sum, so that 32 lanes can each take every 32nd word; the host computes the same value.
+__host__ __device__ __forceinline__ uint64_t fe_mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t issuer_cert_word(uint64_t w, uint32_t i) {
+    return fe_mix64(w + 0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1u));
+}
+__host__ __device__ __forceinline__ uint64_t issuer_cert_finish(uint64_t acc, uint32_t len) {
+    return fe_mix64(acc ^ ((uint64_t)len << 32)) | (1ull << 63);  // never 0
+}
+
+size_t fe_scan_temp_bytes(uint64_t n_items);
+cudaError_t launch_fe_decode(const FeParams& p, void* scan_temp, size_t scan_temp_bytes, int sm_count, cudaStream_t s);
+cudaError_t launch_fe_frame(const FeParams& p, cudaStream_t s);
+cudaError_t launch_fe_issuer(const FeParams& p, const IssuerCertTable& tab, uint64_t* pending, uint64_t pending_mask,
+                             uint32_t* unknown_list, uint32_t unknown_cap, unsigned int* unknown_count, int sm_count, cudaStream_t s);
+cudaError_t launch_fe_finish(const FeParams& p, const uint8_t* status, cudaStream_t s);
 
 }  // namespace ctmr

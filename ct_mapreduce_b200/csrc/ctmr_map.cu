@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256, 4) map_light_kernel(const __grid_constant
     const bool act = e < p.n;
     uint32_t status = CTMR_ST_PARSE_ERR;
     if (act) {
-        const uint64_t off = p.offsets[e], end = p.offsets[e + 1];
+        const uint64_t off = p.offsets[e], end = p.lens ? off + p.lens[e] : p.offsets[e + 1];
         const bool bad_span = end < off || end > p.blob_bytes || end - off > 0x7fffffffull;
         const uint32_t L = bad_span ? 0u : (uint32_t)(end - off);
         const uint8_t* d = p.blob + off;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
         uint64_t off = 0, end = 0;
         if (act) {
             off = p.offsets[e];
-            end = p.offsets[e + 1];
+            end = p.lens ? off + p.lens[e] : p.offsets[e + 1];
         }
         const bool bad_span = !act || end < off || end > p.blob_bytes || end - off > 0x7fffffffull;
         const uint32_t L = bad_span ? 0u : (uint32_t)(end - off);
@@ -371,21 +371,22 @@ static cudaError_t launch_stream_t(const MapParams& p, int sm_count, int ctas_pe
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kLenBuckets = 256;
 
-__device__ __forceinline__ uint32_t len_bucket(const uint64_t* __restrict__ offsets, uint64_t e, uint64_t blob_bytes) {
-    const uint64_t off = offsets[e], end = offsets[e + 1];
+__device__ __forceinline__ uint32_t len_bucket(const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ lens, uint64_t e,
+                                               uint64_t blob_bytes) {
+    const uint64_t off = offsets[e], end = lens ? off + lens[e] : offsets[e + 1];
     const uint64_t L = (end < off || end > blob_bytes) ? 0 : end - off;
     const uint64_t chunks = (L + 127) >> 7;
     const uint32_t b = chunks >= kLenBuckets ? kLenBuckets - 1 : (uint32_t)chunks;
     return (kLenBuckets - 1) - b;  // bucket 0 = longest
 }
 
-__global__ void __launch_bounds__(256) len_hist_kernel(const uint64_t* __restrict__ offsets, uint64_t n, uint64_t blob_bytes,
+__global__ void __launch_bounds__(256) len_hist_kernel(const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ lens, uint64_t n, uint64_t blob_bytes,
                                                        unsigned int* __restrict__ hist) {
     __shared__ unsigned int sh[kLenBuckets];
     sh[threadIdx.x] = 0;
     __syncthreads();
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(&sh[len_bucket(offsets, e, blob_bytes)], 1u);
+        atomicAdd(&sh[len_bucket(offsets, lens, e, blob_bytes)], 1u);
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
@@ -399,11 +400,11 @@ __global__ void len_scan_kernel(unsigned int* hist_then_cursor) {
     }
 }
 
-__global__ void __launch_bounds__(256) len_scatter_kernel(const uint64_t* __restrict__ offsets, uint64_t n, uint64_t blob_bytes,
+__global__ void __launch_bounds__(256) len_scatter_kernel(const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ lens, uint64_t n, uint64_t blob_bytes,
                                                           unsigned int* __restrict__ cursor, uint32_t* __restrict__ order) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = e < n;
-    const uint32_t b = in ? len_bucket(offsets, e, blob_bytes) : 0xFFFFFFFFu;
+    const uint32_t b = in ? len_bucket(offsets, lens, e, blob_bytes) : 0xFFFFFFFFu;
     const uint32_t peers = __match_any_sync(0xffffffffu, b);
     if (in) {
         const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
@@ -414,15 +415,15 @@ __global__ void __launch_bounds__(256) len_scatter_kernel(const uint64_t* __rest
     }
 }
 
-cudaError_t launch_len_order(const uint64_t* offsets, uint64_t n, uint64_t blob_bytes, unsigned int* hist256, uint32_t* order,
+cudaError_t launch_len_order(const uint64_t* offsets, const uint32_t* lens, uint64_t n, uint64_t blob_bytes, unsigned int* hist256, uint32_t* order,
                              cudaStream_t s) {
     if (!n) return cudaSuccess;
     cudaError_t err = cudaMemsetAsync(hist256, 0, kLenBuckets * sizeof(unsigned int), s);
     if (err != cudaSuccess) return err;
     const unsigned hb = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
-    len_hist_kernel<<<hb < 148u * 8u ? (hb ? hb : 1u) : 148u * 8u, 256, 0, s>>>(offsets, n, blob_bytes, hist256);
+    len_hist_kernel<<<hb < 148u * 8u ? (hb ? hb : 1u) : 148u * 8u, 256, 0, s>>>(offsets, lens, n, blob_bytes, hist256);
     len_scan_kernel<<<1, 1, 0, s>>>(hist256);
-    len_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(offsets, n, blob_bytes, hist256, order);
+    len_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(offsets, lens, n, blob_bytes, hist256, order);
     return cudaGetLastError();
 }
 
@@ -477,6 +478,7 @@ cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {
     static const int warps = env_int("CTMR_MAP_WARPS", 8);
     static const int chunk = env_int("CTMR_MAP_CHUNK", 128);
     static const int cps = env_int("CTMR_MAP_CTAS_PER_SM", 0);
+    if (variant != 2 && p.lens) return cudaErrorNotSupported;  // only the streaming kernel takes explicit lengths
     if (variant == 1) return launch_map_v1(p, sm_count, s);
     if (variant == 3) return launch_map_v3(p, sm_count, s);
     if (loader == 1) {

@@ -56,6 +56,26 @@ class KnownCertificatesView:
         return out.value
 
 
+class RawBatchResult:
+    """Outputs of ctmr_process_raw (ctmr_raw_out): the path's outputs plus what the wire format carried."""
+
+    def __init__(self, n: int, want_sha: bool = True, want_meta: bool = False):
+        self.path = BatchResult(np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8) if want_sha else None, np.zeros(n, np.int64),
+                                np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.uint8))
+        if want_meta:
+            p = self.path
+            p.issuer_name_off, p.issuer_name_len = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+            p.crldp_off, p.crldp_len = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+            p.first_issuer_dn, p.first_crldp = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        self.entry_status = np.zeros(n, np.uint8)
+        self.entry_type = np.zeros(n, np.uint8)
+        self.timestamp_ms = np.zeros(n, np.uint64)
+        self.issuer = np.zeros(n, np.uint32)
+        self.leaf_src = np.zeros(n, np.uint8)
+        self.leaf_off = np.zeros(n, np.uint32)
+        self.leaf_len = np.zeros(n, np.uint32)
+
+
 class GpuCertDatabase:
     """One ctmr_ctx = one GPU's share of the known-certificate state."""
 
@@ -158,6 +178,35 @@ class GpuCertDatabase:
                                                  capi.ptr(issuer_offsets) if n_iss else None, n_iss,
                                                  capi.ptr(issuer_idx), now_unix_ns, C.byref(o)))
         return out
+
+    # ------------------------------------------------------------------ CT wire-format front end (include/ctmr_frontend.h)
+    def store_raw_entries(self, text, leaf_off, leaf_len, extra_off, extra_len, now_unix_ns: int, want_sha: bool = True,
+                          want_meta: bool = False) -> "RawBatchResult":
+        """get-entries strings (base64 leaf_input / extra_data, spans into `text`) through ctmr_process_raw:
+        what GetRawEntries' JSON decode, ct.LogEntryFromLeaf (ct-fetch.go:424,452) and insertCTWorker + Store do."""
+        text = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, np.uint8)
+        leaf_off, extra_off = np.ascontiguousarray(leaf_off, np.uint64), np.ascontiguousarray(extra_off, np.uint64)
+        leaf_len, extra_len = np.ascontiguousarray(leaf_len, np.uint32), np.ascontiguousarray(extra_len, np.uint32)
+        n = leaf_off.size
+        r = RawBatchResult(n, want_sha, want_meta)
+        p = r.path
+        o = capi.RawOut()
+        o.path = capi.Out(capi.ptr(p.status), capi.ptr(p.sha256) if want_sha else None, capi.ptr(p.exp_hour), capi.ptr(p.serial_off),
+                          capi.ptr(p.serial_len), capi.ptr(p.was_unknown), capi.ptr(p.first_issuer_hour),
+                          *([capi.ptr(p.issuer_name_off), capi.ptr(p.issuer_name_len), capi.ptr(p.crldp_off), capi.ptr(p.crldp_len),
+                             capi.ptr(p.first_issuer_dn), capi.ptr(p.first_crldp)] if want_meta else [None] * 6))
+        for name in ("entry_status", "entry_type", "timestamp_ms", "issuer", "leaf_src", "leaf_off", "leaf_len"):
+            setattr(o, name, capi.ptr(getattr(r, name)))
+        b = capi.RawBatch(capi.ptr(text), text.size, capi.ptr(leaf_off), capi.ptr(leaf_len), capi.ptr(extra_off), capi.ptr(extra_len),
+                          n, now_unix_ns)
+        self._check(self._lib.ctmr_process_raw(self._h, C.byref(b), C.byref(o)))
+        return r
+
+    def frontend_profile_last(self):
+        """(frontend_ms, path_ms, frontend_launches) of the last store_raw_entries call (CUDA events inside the library)."""
+        a, b, k = C.c_float(0), C.c_float(0), C.c_uint64(0)
+        self._check(self._lib.ctmr_frontend_profile_last(self._h, C.byref(a), C.byref(b), C.byref(k)))
+        return a.value, b.value, k.value
 
     # ------------------------------------------------------------------ device-resident variants (torch tensors / raw pointers)
     def map_device(self, batch: capi.DevBatch, out: capi.DevOut, stream=None):

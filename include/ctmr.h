@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CTMR_ABI_VERSION 1
+#define CTMR_ABI_VERSION 2
 
 /* ---- batch-level return codes ------------------------------------------------------------ */
 enum {
@@ -190,6 +190,9 @@ typedef struct ctmr_dev_batch {
     uint32_t reserved;
     uint64_t first_index;       /* global index of entry 0 */
     int64_t now_unix_ns;
+    const uint32_t* lens;       /* device [n] or NULL.  When set, entry i = blob[offsets[i] .. offsets[i]+lens[i]):
+                                 * records need not be contiguous and offsets needs only n elements (this is how
+                                 * the wire-format front end, ctmr_frontend.h, hands over leaves it decoded in place) */
 } ctmr_dev_batch;
 
 typedef struct ctmr_dev_out { /* device pointers, each [n]; NULL = not produced */

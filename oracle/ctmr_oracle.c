@@ -215,13 +215,9 @@ static int walk_name(const uint8_t* d, size_t pos, size_t end, ora_cert* out, in
     return 0;
 }
 
-int ora_parse_cert(const uint8_t* d, size_t len, ora_cert* out) {
-    memset(out, 0, sizeof *out);
-    tlv_t cert, tbs, t;
-    /* x509.ParseCertificate: asn1.Unmarshal into certificate{}, trailing data is an error */
-    if (read_tlv(d, 0, len, &cert) || cert.tag != 0x30) return -1;
-    if ((size_t)cert.hdr + cert.len != len) return -1;
-    size_t cend = len, pos = cert.hdr;
+/* TBSCertificate at d[pos..cend): everything parseCertificate reads from it.  *tbs_end = offset just past it. */
+static int parse_tbs(const uint8_t* d, size_t pos, size_t cend, ora_cert* out, size_t* tbs_end) {
+    tlv_t tbs, t;
     if (read_tlv(d, pos, cend, &tbs) || tbs.tag != 0x30) return -1;
     out->tbs_off = (uint32_t)pos;
     out->tbs_len = tbs.hdr + tbs.len;
@@ -347,11 +343,34 @@ int ora_parse_cert(const uint8_t* d, size_t len, ora_cert* out) {
         }
     }
     /* encoding/asn1 tolerates extra trailing elements inside a SEQUENCE parsed into a struct */
-    pos += tbs.hdr + tbs.len;
+    *tbs_end = pos + tbs.hdr + tbs.len;
+    return 0;
+}
+
+int ora_parse_cert(const uint8_t* d, size_t len, ora_cert* out) {
+    memset(out, 0, sizeof *out);
+    tlv_t cert, t;
+    /* x509.ParseCertificate: asn1.Unmarshal into certificate{}, trailing data is an error */
+    if (read_tlv(d, 0, len, &cert) || cert.tag != 0x30) return -1;
+    if ((size_t)cert.hdr + cert.len != len) return -1;
+    size_t cend = len, pos = cert.hdr;
+    int rc = parse_tbs(d, pos, cend, out, &pos);
+    if (rc) return rc;
     if (read_tlv(d, pos, cend, &t) || t.tag != 0x30) return -11; /* signatureAlgorithm */
     pos += t.hdr + t.len;
     if (read_tlv(d, pos, cend, &t) || t.tag != 0x03 || t.len == 0) return -12; /* signatureValue */
     return 0;
+}
+
+/* ct-go x509.ParseTBSCertificate (used by MerkleTreeLeaf.Precertificate(), reached from
+ * ct.LogEntryFromLeaf, cmd/ct-fetch/ct-fetch.go:452): asn1.Unmarshal into tbsCertificate{} with
+ * "trailing data" an error, then the same parseCertificate body as a full certificate. */
+int ora_parse_tbs(const uint8_t* d, size_t len, ora_cert* out) {
+    memset(out, 0, sizeof *out);
+    size_t end = 0;
+    int rc = parse_tbs(d, 0, len, out, &end);
+    if (rc) return rc;
+    return end == len ? 0 : -13;
 }
 
 /* ------------------------------------------------------------------ value types */

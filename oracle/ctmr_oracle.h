@@ -61,6 +61,7 @@ typedef struct ora_cert {
 void ora_sha256(const uint8_t* msg, size_t len, uint8_t out[32]);
 size_t ora_b64url(const uint8_t* in, size_t n, char* out); /* padded URL alphabet; NUL-terminates */
 int ora_parse_cert(const uint8_t* der, size_t len, ora_cert* out); /* 0 = ok, <0 = parse error */
+int ora_parse_tbs(const uint8_t* tbs, size_t len, ora_cert* out);  /* ct-go x509.ParseTBSCertificate; offsets relative to tbs */
 
 void ora_issuer_id(const uint8_t* spki, size_t len, uint8_t digest[32], char id[45]);
 int64_t ora_exp_hour(int64_t not_after_sec);
@@ -119,6 +120,22 @@ void ora_db_filter_counters(ora_db*, uint64_t out[8]); /* indexed by status code
 /* timed CPU arm: map-only over a batch (parse + filter + both SHA-256), returns entries kept */
 uint64_t ora_map_only(const uint8_t* blob, const uint64_t* offsets, uint64_t n, const uint8_t* filter,
                       size_t filter_len, int log_expired, int64_t now_unix_ns, int nthreads, uint8_t* sha_out);
+
+/* ---- CT wire-format front end (ctmr_oracle_frontend.c) ---- */
+enum { /* same numeric values as CTMR_FE_* in include/ctmr_frontend.h */
+    ORA_FE_OK = 0, ORA_FE_BAD_BASE64 = 1, ORA_FE_BAD_LEAF = 2, ORA_FE_UNKNOWN_TYPE = 3, ORA_FE_BAD_EXTRA = 4, ORA_FE_BAD_CERT = 5
+};
+typedef struct ora_entry {
+    uint64_t timestamp_ms;            /* TimestampedEntry.timestamp */
+    uint32_t entry_type;              /* 0 x509_entry, 1 precert_entry, 0xFF anything else */
+    uint32_t leaf_src;                /* certificate insertCTWorker processes: 0 = inside leaf_input, 1 = inside extra_data */
+    uint32_t leaf_off, leaf_len;
+    uint32_t chain0_off, chain0_len;  /* Chain[0] inside extra_data; len 0 = empty chain */
+    uint32_t chain_count;
+    uint32_t tbs_off, tbs_len;        /* precert entries: TBSCertificate inside leaf_input */
+} ora_entry;
+long ora_b64_decode(const uint8_t* in, size_t n, uint8_t* out, size_t cap); /* base64.StdEncoding; -1 = corrupt input */
+int ora_entry_from_leaf(const uint8_t* leaf_input, size_t nl, const uint8_t* extra_data, size_t ne, ora_entry* e); /* ORA_FE_* */
 
 /* synthetic corpus (ct_mapreduce_b200/csrc/ctmr_synth.h) on the CPU */
 struct ctmr_synth_cfg;

@@ -47,6 +47,12 @@ class OraCert(C.Structure):
         ("is_ca", C.c_int32)]
 
 
+class OraEntry(C.Structure):
+    _fields_ = [("timestamp_ms", C.c_uint64), ("entry_type", C.c_uint32), ("leaf_src", C.c_uint32),
+                ("leaf_off", C.c_uint32), ("leaf_len", C.c_uint32), ("chain0_off", C.c_uint32), ("chain0_len", C.c_uint32),
+                ("chain_count", C.c_uint32), ("tbs_off", C.c_uint32), ("tbs_len", C.c_uint32)]
+
+
 class OraOut(C.Structure):
     _fields_ = [("status", C.c_void_p), ("sha256", C.c_void_p), ("exp_hour", C.c_void_p), ("serial_off", C.c_void_p),
                 ("serial_len", C.c_void_p), ("was_unknown", C.c_void_p), ("first_issuer_hour", C.c_void_p),
@@ -56,8 +62,9 @@ class OraOut(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (Makefile in this directory)."""
-    if force or not os.path.exists(_LIB_PATH):
-        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    if force:
+        subprocess.run(["make", "-C", _HERE, "clean"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)  # incremental: a no-op when up to date
     return _LIB_PATH
 
 
@@ -93,6 +100,9 @@ def lib():
         L.ora_db_set_cardinality.argtypes = [vp, i64, vp]; L.ora_db_set_cardinality.restype = u64
         L.ora_db_filter_counters.argtypes = [vp, vp]
         L.ora_map_only.argtypes = [vp, vp, u64, vp, sz, C.c_int, i64, C.c_int, vp]; L.ora_map_only.restype = u64
+        L.ora_parse_tbs.argtypes = [vp, sz, C.POINTER(OraCert)]; L.ora_parse_tbs.restype = C.c_int
+        L.ora_b64_decode.argtypes = [vp, sz, vp, sz]; L.ora_b64_decode.restype = C.c_long
+        L.ora_entry_from_leaf.argtypes = [vp, sz, vp, sz, C.POINTER(OraEntry)]; L.ora_entry_from_leaf.restype = C.c_int
         L.ora_synth_lengths.argtypes = [C.POINTER(SynthCfg), u64, u64, vp]; L.ora_synth_lengths.restype = u64
         L.ora_synth_write.argtypes = [C.POINTER(SynthCfg), u64, u64, vp, vp]
         L.ora_synth_issuer_idx.argtypes = [C.POINTER(SynthCfg), u64, u64, vp]
@@ -300,3 +310,83 @@ def synth_issuers(cfg: SynthCfg):
     blob = np.zeros(total, np.uint8)
     lib().ora_synth_issuers(C.byref(cfg), _p(offsets), _p(blob), total)
     return blob, offsets
+
+
+# ---------------------------------------------------------------- CT wire-format front end
+
+FE_OK, FE_BAD_BASE64, FE_BAD_LEAF, FE_UNKNOWN_TYPE, FE_BAD_EXTRA, FE_BAD_CERT = range(6)
+
+
+def b64_decode(text: bytes):
+    """base64.StdEncoding as encoding/json applies it to []byte fields; None = corrupt input."""
+    src = (C.c_uint8 * max(1, len(text))).from_buffer_copy(text or b"\0")
+    out = (C.c_uint8 * (len(text) // 4 * 3 + 3))()
+    n = lib().ora_b64_decode(src, len(text), out, len(out))
+    return None if n < 0 else bytes(out[:n])
+
+
+def parse_tbs(tbs: bytes):
+    c = OraCert()
+    buf = (C.c_uint8 * max(1, len(tbs))).from_buffer_copy(tbs or b"\0")
+    return lib().ora_parse_tbs(buf, len(tbs), C.byref(c)), c
+
+
+def entry_from_leaf(leaf_input: bytes, extra_data: bytes):
+    """ct.LogEntryFromLeaf on decoded bytes -> (ORA_FE_*, OraEntry)."""
+    e = OraEntry()
+    a = (C.c_uint8 * max(1, len(leaf_input))).from_buffer_copy(leaf_input or b"\0")
+    b = (C.c_uint8 * max(1, len(extra_data))).from_buffer_copy(extra_data or b"\0")
+    return lib().ora_entry_from_leaf(a, len(leaf_input), b, len(extra_data), C.byref(e)), e
+
+
+class RawResult:
+    pass
+
+
+def raw_process(db: "DB", text: bytes, leaf_off, leaf_len, extra_off, extra_len, now_ns: int) -> RawResult:
+    """get-entries strings -> what the reference's downloader + worker + Store do with them, entry by entry
+    (cmd/ct-fetch/ct-fetch.go:446-484 then :191-245), through the sequential oracle DB."""
+    n = len(leaf_off)
+    r = RawResult()
+    r.entry_status = np.zeros(n, np.uint8)
+    r.entry_type = np.full(n, 0xFF, np.uint8)
+    r.timestamp_ms = np.zeros(n, np.uint64)
+    r.leaf_src = np.zeros(n, np.uint8)
+    r.leaf_off = np.zeros(n, np.uint32)
+    r.leaf_len = np.zeros(n, np.uint32)
+    r.issuer_der = [None] * n          # Chain[0] bytes of entries that reached the worker with a chain
+    leaves, issuers, issuer_pos, issuer_idx = [], [], {}, np.full(n, 0xFFFFFFFF, np.uint32)
+    for i in range(n):
+        li = b64_decode(text[int(leaf_off[i]):int(leaf_off[i]) + int(leaf_len[i])])
+        ed = b64_decode(text[int(extra_off[i]):int(extra_off[i]) + int(extra_len[i])])
+        leaf = b""
+        if li is None or ed is None:
+            r.entry_status[i] = FE_BAD_BASE64
+        else:
+            st, e = entry_from_leaf(li, ed)
+            r.entry_status[i] = st
+            r.entry_type[i] = e.entry_type
+            r.timestamp_ms[i] = e.timestamp_ms
+            if st == FE_OK or (st == FE_BAD_CERT and e.entry_type == 0):
+                # an x509 leaf that fails to parse is dropped by the downloader; the GPU path reports it as
+                # status PARSE_ERR from the same bytes, so the oracle hands the bytes over as well
+                src = ed if e.leaf_src else li
+                leaf = src[e.leaf_off:e.leaf_off + e.leaf_len]
+                r.leaf_src[i], r.leaf_off[i], r.leaf_len[i] = e.leaf_src, e.leaf_off, e.leaf_len
+                if e.chain0_len and st == FE_OK:
+                    ch = ed[e.chain0_off:e.chain0_off + e.chain0_len]
+                    r.issuer_der[i] = ch
+                    k = issuer_pos.get(ch)
+                    if k is None:
+                        k = issuer_pos[ch] = len(issuers)
+                        issuers.append(ch)
+                    issuer_idx[i] = k
+        leaves.append(leaf)
+    offsets = np.zeros(n + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(x) for x in leaves], dtype=np.uint64)
+    blob = np.frombuffer(b"".join(leaves) or b"\0", np.uint8)
+    ioffs = np.zeros(len(issuers) + 1, np.uint64)
+    ioffs[1:] = np.cumsum([len(x) for x in issuers], dtype=np.uint64)
+    iblob = np.frombuffer(b"".join(issuers) or b"\0", np.uint8)
+    r.path = db.process(blob, offsets, iblob, ioffs, issuer_idx, now_ns)
+    return r

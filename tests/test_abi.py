@@ -17,7 +17,7 @@ def lib():
 
 
 def _declared_functions():
-    text = open(os.path.join(ROOT, "include", "ctmr.h")).read()
+    text = open(os.path.join(ROOT, "include", "ctmr.h")).read() + open(os.path.join(ROOT, "include", "ctmr_frontend.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ctmr_[a-z0-9_]+)\s*\(", text)))
 
@@ -35,7 +35,7 @@ def test_python_binding_covers_header(lib):
 
 
 def test_abi_version(lib):
-    assert lib.ctmr_abi_version() == 1
+    assert lib.ctmr_abi_version() == 2  # 2: ctmr_dev_batch.lens, ctmr_frontend.h
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -43,16 +43,18 @@ def test_struct_layouts_match_header(tmp_path):
     import subprocess
     from ct_mapreduce_b200 import capi
     src = tmp_path / "probe.c"
-    src.write_text('#include "include/ctmr.h"\n#include "ct_mapreduce_b200/csrc/ctmr_synth.h"\n#include <stdio.h>\n'
-                   '#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ctmr_config), sizeof(ctmr_out),'
+    src.write_text('#include "include/ctmr_frontend.h"\n#include "ct_mapreduce_b200/csrc/ctmr_synth.h"\n#include <stdio.h>\n'
+                   '#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ctmr_config), sizeof(ctmr_out),'
                    'sizeof(ctmr_dev_batch), sizeof(ctmr_dev_out), sizeof(ctmr_synth_cfg), sizeof(ctmr_key),'
-                   'offsetof(ctmr_key, serial), offsetof(ctmr_key, valid));return 0;}\n')
+                   'offsetof(ctmr_key, serial), offsetof(ctmr_key, valid), sizeof(ctmr_raw_batch), sizeof(ctmr_raw_out),'
+                   'offsetof(ctmr_raw_out, entry_status), offsetof(ctmr_dev_batch, lens));return 0;}\n')
     exe = tmp_path / "probe"
     subprocess.run(["gcc", "-I", ROOT, str(src), "-o", str(exe)], check=True, cwd=ROOT)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert got == [C.sizeof(capi.Config), C.sizeof(capi.Out), C.sizeof(capi.DevBatch), C.sizeof(capi.DevOut),
                    C.sizeof(capi.SynthCfg), capi.KEY_DTYPE.itemsize, capi.KEY_DTYPE.fields["serial"][1],
-                   capi.KEY_DTYPE.fields["valid"][1]]
+                   capi.KEY_DTYPE.fields["valid"][1], C.sizeof(capi.RawBatch), C.sizeof(capi.RawOut),
+                   capi.RawOut.entry_status.offset, capi.DevBatch.lens.offset]
     assert capi.KEY_DTYPE.itemsize == 64
 
 
