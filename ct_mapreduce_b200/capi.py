@@ -45,7 +45,8 @@ class Config(C.Structure):
 class Out(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("status", "sha256", "exp_hour", "serial_off", "serial_len", "was_unknown", "first_issuer_hour",
-                 "issuer_name_off", "issuer_name_len", "crldp_off", "crldp_len", "first_issuer_dn", "first_crldp")]
+                 "issuer_name_off", "issuer_name_len", "crldp_off", "crldp_len", "first_issuer_dn", "first_crldp")] + \
+               [("pem", C.c_void_p), ("pem_cap", C.c_uint64), ("pem_off", C.c_void_p)]
 
 
 class DevBatch(C.Structure):

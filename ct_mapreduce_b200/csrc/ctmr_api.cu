@@ -25,6 +25,16 @@ constexpr uint64_t kStageBytes = 768ull << 20;  // leaf bytes per pipeline stage
 
 thread_local std::string g_create_error;
 
+// device side of the PEM output (ctmr_out.pem): one per host-pipeline stage and one for the front end
+struct PemStage {
+    uint64_t cap_entries = 0, cap_bytes = 0;
+    uint64_t *sizes = nullptr, *off = nullptr;
+    uint8_t* text = nullptr;
+    void* scan_temp = nullptr;
+    size_t scan_temp_bytes = 0;
+    std::vector<uint64_t> host_off;
+};
+
 struct Stage {
     cudaStream_t stream = nullptr;
     cudaEvent_t reduced = nullptr;  // recorded after this stage's resolve kernel
@@ -46,15 +56,26 @@ struct Stage {
     uint32_t* spans = nullptr;       // [4][E]: issuer name off/len, crldp off/len
     uint32_t* meta_slots = nullptr;  // [2*E]
     uint8_t* first_meta = nullptr;   // [2][E]: first_issuer_dn, first_crldp
+    PemStage pem;                    // allocated when a caller first asks for PEM output
+};
+
+// one upload stage of the front end: a chunk's characters and string spans, device side and pinned host staging
+struct FeStage {
+    uint8_t* text = nullptr;  // [16 + cap_text + 64]
+    uint64_t *leaf_off = nullptr, *extra_off = nullptr, *h_leaf_off = nullptr, *h_extra_off = nullptr;
+    uint32_t *leaf_len = nullptr, *extra_len = nullptr, *h_leaf_len = nullptr, *h_extra_len = nullptr;
+    cudaEvent_t uploaded = nullptr, consumed = nullptr;
+    std::vector<uint8_t> pack;  // host staging of the slow path (strings scattered over more than one chunk of text)
 };
 
 // CT wire-format front end (include/ctmr_frontend.h): device buffers of one chunk + the device mirror of
 // the issuer registry keyed by certificate bytes
 struct FrontEnd {
     uint64_t cap_entries = 0, cap_text = 0, cap_decoded = 0;
-    uint8_t* text = nullptr;  // [16 + cap_text + 64]
-    uint64_t *leaf_off = nullptr, *extra_off = nullptr, *pad_size = nullptr, *dec_off = nullptr;
-    uint32_t *leaf_len = nullptr, *extra_len = nullptr, *dec_len = nullptr;
+    FeStage stage[2];          // upload double buffer
+    cudaStream_t copy_stream = nullptr;
+    uint64_t *pad_size = nullptr, *dec_off = nullptr;
+    uint32_t* dec_len = nullptr;
     uint8_t *str_bad = nullptr, *decoded = nullptr;
     void* scan_temp = nullptr;
     size_t scan_temp_bytes = 0;
@@ -79,7 +100,7 @@ struct FrontEnd {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     float fe_ms = 0.f, path_ms = 0.f;
     uint64_t launches = 0;
-    std::vector<uint8_t> pack;  // host staging of the slow path (strings scattered over more than one chunk of text)
+    PemStage pem;
 };
 
 }  // namespace
@@ -127,6 +148,7 @@ struct ctmr_ctx {
 namespace {
 
 void fe_destroy(ctmr_ctx* c);
+void pem_free(PemStage& ps);
 int fe_add_issuer(ctmr_ctx* c, const std::string& der, uint32_t idx);
 int fe_clear_issuers(ctmr_ctx* c);
 
@@ -279,18 +301,64 @@ int reduce_on(ctmr_ctx* c, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, 
 }
 
 
+// ------------------------------------------------------------------------------------------------ PEM output
+void pem_free(PemStage& ps) {
+    cudaFree(ps.sizes); cudaFree(ps.off); cudaFree(ps.text); cudaFree(ps.scan_temp);
+    ps = PemStage{};
+}
+
+int pem_ensure(ctmr_ctx* c, PemStage& ps, uint64_t entries, uint64_t der_bytes) {
+    const uint64_t need_bytes = der_bytes / 3 * 4 + der_bytes / 48 + 64 * entries + 256;  // body + newlines + boundary lines
+    if (ps.cap_entries >= entries && ps.cap_bytes >= need_bytes) return CTMR_OK;
+    CU(c, cudaDeviceSynchronize());
+    pem_free(ps);
+    CU(c, cudaMalloc(&ps.sizes, (entries + 1) * 8));
+    CU(c, cudaMalloc(&ps.off, (entries + 1) * 8));
+    CU(c, cudaMalloc(&ps.text, need_bytes));
+    ps.scan_temp_bytes = pem_scan_temp_bytes(entries + 1);
+    CU(c, cudaMalloc(&ps.scan_temp, ps.scan_temp_bytes ? ps.scan_temp_bytes : 16));
+    ps.cap_entries = entries;
+    ps.cap_bytes = need_bytes;
+    return CTMR_OK;
+}
+
+// Encodes the selected certificates of one chunk on `s`, waits for it, and appends the text to the caller's
+// buffer at *base (host).  pem_off_out[i] (i < cnt) = absolute start of entry i's text.
+int pem_chunk(ctmr_ctx* c, PemStage& ps, const uint8_t* blob, const uint64_t* offsets, const uint32_t* lens, const uint8_t* select,
+              uint64_t cnt, const ctmr_out* out, uint64_t first, uint64_t* base, cudaStream_t s) {
+    CU(c, launch_pem_encode(blob, offsets, lens, select, cnt, ps.sizes, ps.scan_temp, ps.scan_temp_bytes, ps.off, ps.text, ps.cap_bytes,
+                            c->st.error_flag, c->sm_count, s));
+    ps.host_off.resize(cnt + 1);
+    CU(c, cudaMemcpyAsync(ps.host_off.data(), ps.off, (cnt + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    const uint64_t total = ps.host_off[cnt];
+    if (total > ps.cap_bytes) return fail(c, CTMR_E_BATCH_TOO_LARGE, "PEM staging too small (internal sizing)");
+    if (*base + total > out->pem_cap) return fail(c, CTMR_E_BATCH_TOO_LARGE, "ctmr_out.pem_cap too small for the new certificates' PEM");
+    if (total) CU(c, cudaMemcpyAsync(out->pem + *base, ps.text, total, cudaMemcpyDeviceToHost, s));
+    for (uint64_t i = 0; i < cnt; ++i) out->pem_off[first + i] = *base + ps.host_off[i];
+    *base += total;
+    return CTMR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ front end plumbing
 void fe_destroy(ctmr_ctx* c) {
     FrontEnd* f = c->fe;
     if (!f) return;
-    cudaFree(f->text); cudaFree(f->leaf_off); cudaFree(f->extra_off); cudaFree(f->pad_size); cudaFree(f->dec_off);
-    cudaFree(f->leaf_len); cudaFree(f->extra_len); cudaFree(f->dec_len); cudaFree(f->str_bad); cudaFree(f->decoded);
+    for (FeStage& st : f->stage) {
+        cudaFree(st.text); cudaFree(st.leaf_off); cudaFree(st.extra_off); cudaFree(st.leaf_len); cudaFree(st.extra_len);
+        cudaFreeHost(st.h_leaf_off); cudaFreeHost(st.h_extra_off); cudaFreeHost(st.h_leaf_len); cudaFreeHost(st.h_extra_len);
+        if (st.uploaded) cudaEventDestroy(st.uploaded);
+        if (st.consumed) cudaEventDestroy(st.consumed);
+    }
+    if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
+    cudaFree(f->pad_size); cudaFree(f->dec_off); cudaFree(f->dec_len); cudaFree(f->str_bad); cudaFree(f->decoded);
     cudaFree(f->scan_temp); cudaFree(f->entry_status); cudaFree(f->entry_type); cudaFree(f->leaf_src); cudaFree(f->timestamp);
     cudaFree(f->leaf_abs); cudaFree(f->chain_abs); cudaFree(f->tbs_abs); cudaFree(f->leaf_rel); cudaFree(f->leaf_len_out);
     cudaFree(f->chain_len); cudaFree(f->tbs_len); cudaFree(f->issuer_idx); cudaFree(f->status); cudaFree(f->sha);
     cudaFree(f->was_unknown); cudaFree(f->first); cudaFree(f->first_meta); cudaFree(f->exp_hour); cudaFree(f->serial_off);
     cudaFree(f->serial_len); cudaFree(f->spans); cudaFree(f->slots_dev); cudaFree(f->arena); cudaFree(f->pending);
     cudaFree(f->unknown_list); cudaFree(f->unknown_count);
+    pem_free(f->pem);
     if (f->ev0) cudaEventDestroy(f->ev0);
     if (f->ev1) cudaEventDestroy(f->ev1);
     if (f->ev2) cudaEventDestroy(f->ev2);
@@ -385,8 +453,22 @@ int ensure_frontend(ctmr_ctx* c) {
             return bail(e_ == cudaErrorMemoryAllocation ? CTMR_E_NOMEM : CTMR_E_CUDA);      \
         }                                                                                  \
     } while (0)
-    FEM(f->text, 16 + T + 64);
-    FEM(f->leaf_off, E * 8); FEM(f->extra_off, E * 8); FEM(f->leaf_len, E * 4); FEM(f->extra_len, E * 4);
+    for (FeStage& st : f->stage) {
+        FEM(st.text, 16 + T + 64);
+        FEM(st.leaf_off, E * 8); FEM(st.extra_off, E * 8); FEM(st.leaf_len, E * 4); FEM(st.extra_len, E * 4);
+        if (cudaMallocHost(&st.h_leaf_off, E * 8) != cudaSuccess || cudaMallocHost(&st.h_extra_off, E * 8) != cudaSuccess ||
+            cudaMallocHost(&st.h_leaf_len, E * 4) != cudaSuccess || cudaMallocHost(&st.h_extra_len, E * 4) != cudaSuccess ||
+            cudaEventCreateWithFlags(&st.uploaded, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming) != cudaSuccess ||
+            cudaMemsetAsync(st.text, 0, 16 + T + 64, c->stream) != cudaSuccess) {
+            fail(c, CTMR_E_NOMEM, "front end: staging allocation failed");
+            return bail(CTMR_E_NOMEM);
+        }
+    }
+    if (cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail(c, CTMR_E_CUDA, "front end: stream creation failed");
+        return bail(CTMR_E_CUDA);
+    }
     FEM(f->pad_size, (2 * E + 1) * 8); FEM(f->dec_off, (2 * E + 1) * 8); FEM(f->dec_len, 2 * E * 4); FEM(f->str_bad, 2 * E);
     FEM(f->decoded, f->cap_decoded);
     f->scan_temp_bytes = fe_scan_temp_bytes(2 * E + 1);
@@ -406,7 +488,7 @@ int ensure_frontend(ctmr_ctx* c) {
     FEM(f->unknown_count, 16);
 #undef FEM
     if (cudaMemsetAsync(f->slots_dev, 0, (f->slot_mask + 1) * sizeof(IssuerCertSlot), c->stream) != cudaSuccess ||
-        cudaMemsetAsync(f->text, 0, 16 + T + 64, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess ||
         cudaEventCreate(&f->ev0) != cudaSuccess ||
         cudaEventCreate(&f->ev1) != cudaSuccess || cudaEventCreate(&f->ev2) != cudaSuccess) {
         fail(c, CTMR_E_CUDA, "front end: initialisation failed");
@@ -519,6 +601,7 @@ void ctmr_destroy(ctmr_ctx* c) {
         cudaFree(s.blob); cudaFree(s.offsets); cudaFree(s.issuer_idx); cudaFree(s.status); cudaFree(s.sha);
         cudaFree(s.exp_hour); cudaFree(s.serial_off); cudaFree(s.serial_len); cudaFree(s.was_unknown); cudaFree(s.first);
         cudaFree(s.keys); cudaFree(s.slot_of); cudaFree(s.pair_slot); cudaFree(s.order); cudaFree(s.len_hist); cudaFree(s.spans); cudaFree(s.meta_slots); cudaFree(s.first_meta);
+        pem_free(s.pem);
         if (s.reduced) cudaEventDestroy(s.reduced);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -844,6 +927,9 @@ int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets
     uint64_t lo = 0;
     int sub = 0;
     cudaEvent_t prev = nullptr;
+    const bool want_pem = out->pem != nullptr || out->pem_off != nullptr;
+    if (want_pem && !(out->pem && out->pem_off)) return fail(c, CTMR_E_INVALID, "pem and pem_off go together");
+    uint64_t pem_base = 0;
     while (lo < n) {
         uint64_t hi = lo + c->stage_entries < n ? lo + c->stage_entries : n;
         if (offsets[hi] - offsets[lo] > c->stage_bytes) {  // shrink to the byte budget
@@ -916,10 +1002,17 @@ int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets
         if (out->serial_len) CU(c, cudaMemcpyAsync(out->serial_len + lo, s.serial_len, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
         if (out->was_unknown) CU(c, cudaMemcpyAsync(out->was_unknown + lo, s.was_unknown, cnt, cudaMemcpyDeviceToHost, s.stream));
         if (out->first_issuer_hour) CU(c, cudaMemcpyAsync(out->first_issuer_hour + lo, s.first, cnt, cudaMemcpyDeviceToHost, s.stream));
+        if (want_pem) {  // StoreCertificatePEM's argument for this slice's new certificates (the host waits for this slice here)
+            rc = pem_ensure(c, s.pem, c->stage_entries, c->stage_bytes);
+            if (rc) return rc;
+            rc = pem_chunk(c, s.pem, db.blob, s.offsets, nullptr, s.was_unknown, cnt, out, lo, &pem_base, s.stream);
+            if (rc) return rc;
+        }
         lo = hi;
         ++sub;
     }
     for (int k = 0; k < kStages && k < sub; ++k) CU(c, cudaStreamSynchronize(c->stages[k].stream));
+    if (want_pem) out->pem_off[n] = pem_base;
     c->next_index += n;
     // pairs of stage s read the pair table after resolve(s); a later stage's resolve only ever
     // raises inv_first for lower indices, which cannot exist: indices grow with the stage number.
@@ -1141,10 +1234,17 @@ int ctmr_process_raw(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {
     cudaStream_t s = c->stream;
     const ctmr_out* po = &out->path;
     const bool want_meta = po->first_issuer_dn || po->first_crldp || po->issuer_name_off || po->crldp_off;
+    const bool want_pem = po->pem != nullptr || po->pem_off != nullptr;
+    if (want_pem && !(po->pem && po->pem_off)) return fail(c, CTMR_E_INVALID, "pem and pem_off go together");
+    uint64_t pem_base = 0;
     const uint64_t E = f->cap_entries;
-    std::vector<uint64_t> lo_off, ex_off;  // chunk-relative string offsets
-    uint64_t lo = 0;
-    while (lo < b->n) {
+    // Two upload stages: while chunk k runs (and waits on its host round trips), chunk k+1's text and spans
+    // are already crossing PCIe on the copy stream.
+    struct Plan {
+        uint64_t lo = 0, hi = 0, text_bytes = 0;
+    };
+    auto upload = [&](uint64_t lo, int which, Plan& pl) -> int {
+        FeStage& st = f->stage[which];
         // ---- chunk = as many entries as fit the entry and character budgets
         uint64_t hi = lo, chars = 0, min_off = ~0ull, max_end = 0;
         while (hi < b->n && hi - lo < E) {
@@ -1160,38 +1260,55 @@ int ctmr_process_raw(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {
         }
         if (hi == lo) return fail(c, CTMR_E_BATCH_TOO_LARGE, "a single entry exceeds the front end's character budget");
         const uint64_t cnt = hi - lo;
-        lo_off.resize(cnt);
-        ex_off.resize(cnt);
-        uint64_t text_bytes = 0;
+        pl.lo = lo;
+        pl.hi = hi;
+        CU(c, cudaStreamWaitEvent(f->copy_stream, st.consumed, 0));  // the decode that last read this stage has run
+        std::memcpy(st.h_leaf_len, b->leaf_input_len + lo, cnt * 4);
+        std::memcpy(st.h_extra_len, b->extra_data_len + lo, cnt * 4);
         if (max_end - min_off <= f->cap_text) {  // strings in place inside the response bodies: one copy
-            text_bytes = max_end - min_off;
+            pl.text_bytes = max_end - min_off;
             for (uint64_t i = 0; i < cnt; ++i) {
-                lo_off[i] = b->leaf_input_off[lo + i] - min_off;
-                ex_off[i] = b->extra_data_off[lo + i] - min_off;
+                st.h_leaf_off[i] = b->leaf_input_off[lo + i] - min_off;
+                st.h_extra_off[i] = b->extra_data_off[lo + i] - min_off;
             }
-            CU(c, cudaMemcpyAsync(f->text + 16, b->text + min_off, text_bytes, cudaMemcpyHostToDevice, s));
+            CU(c, cudaMemcpyAsync(st.text + 16, b->text + min_off, pl.text_bytes, cudaMemcpyHostToDevice, f->copy_stream));
         } else {  // scattered: pack on the host first
-            f->pack.resize(chars);
+            st.pack.resize(chars);
             uint64_t w = 0;
             for (uint64_t i = 0; i < cnt; ++i) {
-                lo_off[i] = w;
-                std::memcpy(f->pack.data() + w, b->text + b->leaf_input_off[lo + i], b->leaf_input_len[lo + i]);
+                st.h_leaf_off[i] = w;
+                std::memcpy(st.pack.data() + w, b->text + b->leaf_input_off[lo + i], b->leaf_input_len[lo + i]);
                 w += b->leaf_input_len[lo + i];
-                ex_off[i] = w;
-                std::memcpy(f->pack.data() + w, b->text + b->extra_data_off[lo + i], b->extra_data_len[lo + i]);
+                st.h_extra_off[i] = w;
+                std::memcpy(st.pack.data() + w, b->text + b->extra_data_off[lo + i], b->extra_data_len[lo + i]);
                 w += b->extra_data_len[lo + i];
             }
-            text_bytes = w;
-            CU(c, cudaMemcpyAsync(f->text + 16, f->pack.data(), text_bytes, cudaMemcpyHostToDevice, s));
+            pl.text_bytes = w;
+            CU(c, cudaMemcpyAsync(st.text + 16, st.pack.data(), pl.text_bytes, cudaMemcpyHostToDevice, f->copy_stream));
         }
-        CU(c, cudaMemcpyAsync(f->leaf_off, lo_off.data(), cnt * 8, cudaMemcpyHostToDevice, s));
-        CU(c, cudaMemcpyAsync(f->extra_off, ex_off.data(), cnt * 8, cudaMemcpyHostToDevice, s));
-        CU(c, cudaMemcpyAsync(f->leaf_len, b->leaf_input_len + lo, cnt * 4, cudaMemcpyHostToDevice, s));
-        CU(c, cudaMemcpyAsync(f->extra_len, b->extra_data_len + lo, cnt * 4, cudaMemcpyHostToDevice, s));
+        CU(c, cudaMemcpyAsync(st.leaf_off, st.h_leaf_off, cnt * 8, cudaMemcpyHostToDevice, f->copy_stream));
+        CU(c, cudaMemcpyAsync(st.extra_off, st.h_extra_off, cnt * 8, cudaMemcpyHostToDevice, f->copy_stream));
+        CU(c, cudaMemcpyAsync(st.leaf_len, st.h_leaf_len, cnt * 4, cudaMemcpyHostToDevice, f->copy_stream));
+        CU(c, cudaMemcpyAsync(st.extra_len, st.h_extra_len, cnt * 4, cudaMemcpyHostToDevice, f->copy_stream));
+        CU(c, cudaEventRecord(st.uploaded, f->copy_stream));
+        return CTMR_OK;
+    };
+    Plan plan[2];
+    rc = upload(0, 0, plan[0]);
+    if (rc) return rc;
+    for (int k = 0;; ++k) {
+        const Plan cur = plan[k & 1];
+        const uint64_t lo = cur.lo, hi = cur.hi, cnt = hi - lo;
+        if (hi < b->n) {  // next chunk's upload overlaps this chunk's kernels
+            rc = upload(hi, (k + 1) & 1, plan[(k + 1) & 1]);
+            if (rc) return rc;
+        }
+        FeStage& st = f->stage[k & 1];
+        CU(c, cudaStreamWaitEvent(s, st.uploaded, 0));
         FeParams p{};
-        p.text = f->text + 16;
-        p.text_bytes = text_bytes;
-        p.leaf_off = f->leaf_off; p.leaf_len = f->leaf_len; p.extra_off = f->extra_off; p.extra_len = f->extra_len;
+        p.text = st.text + 16;
+        p.text_bytes = cur.text_bytes;
+        p.leaf_off = st.leaf_off; p.leaf_len = st.leaf_len; p.extra_off = st.extra_off; p.extra_len = st.extra_len;
         p.n = cnt;
         p.pad_size = f->pad_size; p.dec_off = f->dec_off; p.dec_len = f->dec_len; p.str_bad = f->str_bad; p.decoded = f->decoded;
         p.entry_status = f->entry_status; p.entry_type = f->entry_type; p.timestamp = f->timestamp; p.leaf_src = f->leaf_src;
@@ -1199,6 +1316,7 @@ int ctmr_process_raw(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {
         p.chain_len = f->chain_len; p.tbs_abs = f->tbs_abs; p.tbs_len = f->tbs_len; p.issuer_idx = f->issuer_idx;
         CU(c, cudaEventRecord(f->ev0, s));
         CU(c, launch_fe_decode(p, f->scan_temp, f->scan_temp_bytes, c->sm_count, s));
+        CU(c, cudaEventRecord(st.consumed, s));  // text and spans are dead once decoded: the stage may be refilled
         CU(c, launch_fe_frame(p, s));
         f->launches += 5;  // sizes, scan (cub: one kernel visible to us), decode, frame, tbs
         // ---- Chain[0] -> dense index; certificates never seen before go through ctmr_register_issuers once
@@ -1270,6 +1388,12 @@ int ctmr_process_raw(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {
         CU(c, launch_fe_finish(p, f->status, s));
         ++f->launches;
         CU(c, cudaEventRecord(f->ev2, s));
+        if (want_pem) {  // the decoded DER exists only on the device: its PEM is how new certificates reach the host
+            rc = pem_ensure(c, f->pem, E, f->cap_decoded);
+            if (rc) return rc;
+            rc = pem_chunk(c, f->pem, f->decoded, f->leaf_abs, f->leaf_len_out, f->was_unknown, cnt, po, lo, &pem_base, s);
+            if (rc) return rc;
+        }
 #define FE_D2H(dst, src, bytes) \
     if (dst) CU(c, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(dst) + lo * ((bytes) / cnt), (src), (bytes), cudaMemcpyDeviceToHost, s))
         FE_D2H(po->status, f->status, cnt);
@@ -1301,8 +1425,9 @@ int ctmr_process_raw(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {
         CU(c, cudaEventElapsedTime(&d, f->ev1, f->ev2));
         f->fe_ms += a;
         f->path_ms += d;
-        lo = hi;
+        if (hi >= b->n) break;
     }
+    if (want_pem) po->pem_off[b->n] = pem_base;
     c->next_index += b->n;
     return ctmr_check_device(c, nullptr);
 }

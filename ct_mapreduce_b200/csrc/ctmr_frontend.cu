@@ -343,3 +343,94 @@ cudaError_t launch_fe_finish(const FeParams& p, const uint8_t* status, cudaStrea
 }
 
 }  // namespace ctmr
+
+// ================================================================================================
+// PEM of selected certificates: pem.EncodeToMemory(&pem.Block{Type: "CERTIFICATE",
+// Bytes: cert.Raw}) as built in FilesystemDatabase.Store (storage/filesystemdatabase.go:171-175,197-198),
+// i.e. "-----BEGIN CERTIFICATE-----\n", base64.StdEncoding in lines of 64 characters each ended by '\n',
+// "-----END CERTIFICATE-----\n".  Only NEW certificates are stored, so only they are encoded.
+// ================================================================================================
+namespace ctmr {
+namespace {
+
+constexpr uint32_t kPemHead = 28, kPemTail = 26;  // the two boundary lines, newline included
+
+__device__ __forceinline__ uint32_t pem_size(uint32_t der_len) {
+    const uint32_t b64 = (der_len + 2u) / 3u * 4u;
+    return kPemHead + b64 + (b64 + 63u) / 64u + kPemTail;
+}
+
+__device__ __forceinline__ uint32_t b64_char(uint32_t v) {  // 6 bits -> ASCII of the standard alphabet, branch-free
+    return v + 65u + (v >= 26u ? 6u : 0u) - (v >= 52u ? 75u : 0u) - (v >= 62u ? 15u : 0u) + (v >= 63u ? 3u : 0u);
+}
+
+__global__ void __launch_bounds__(256) pem_sizes_kernel(const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ lens,
+                                                        const uint8_t* __restrict__ select, uint64_t n, uint64_t* __restrict__ sizes) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > n) return;
+    uint64_t sz = 0;
+    if (e < n && select[e]) {
+        const uint64_t len = lens ? lens[e] : offsets[e + 1] - offsets[e];
+        sz = pem_size((uint32_t)len);
+    }
+    sizes[e] = sz;
+}
+
+__global__ void __launch_bounds__(256) pem_encode_kernel(const uint8_t* __restrict__ blob, const uint64_t* __restrict__ offsets,
+                                                         const uint32_t* __restrict__ lens, const uint8_t* __restrict__ select, uint64_t n,
+                                                         const uint64_t* __restrict__ pem_off, uint8_t* __restrict__ pem, uint64_t cap,
+                                                         int* __restrict__ error_flag) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t e = warp0; e < n; e += nwarps) {
+        if (!select[e]) continue;
+        const uint64_t at = pem_off[e];
+        const uint32_t L = lens ? lens[e] : (uint32_t)(offsets[e + 1] - offsets[e]);
+        const uint32_t total = pem_size(L);
+        if (at + total > cap) {  // caller's buffer too small: nothing of this certificate is written
+            if (lane == 0) atomicExch(error_flag, CTMR_E_BATCH_TOO_LARGE);
+            continue;
+        }
+        const uint8_t* d = blob + offsets[e];
+        uint8_t* o = pem + at;
+        const char* head = "-----BEGIN CERTIFICATE-----\n";
+        const char* tail = "-----END CERTIFICATE-----\n";
+        if (lane < kPemHead) o[lane] = (uint8_t)head[lane];
+        if (lane < kPemTail) o[total - kPemTail + lane] = (uint8_t)tail[lane];
+        uint8_t* body = o + kPemHead;
+        const uint32_t ngroups = (L + 2u) / 3u;  // 3 bytes -> 4 characters; 16 groups per line
+        for (uint32_t g = lane; g < ngroups; g += 32u) {
+            const uint32_t i = 3u * g, rem = L - i;
+            const uint32_t b0 = d[i], b1 = rem > 1u ? d[i + 1] : 0u, b2 = rem > 2u ? d[i + 2] : 0u;
+            const uint32_t w = (b0 << 16) | (b1 << 8) | b2;
+            uint8_t* q = body + 4u * g + (g >> 4);  // one '\n' behind every 16 complete groups
+            q[0] = (uint8_t)b64_char(w >> 18);
+            q[1] = (uint8_t)b64_char((w >> 12) & 63u);
+            q[2] = rem > 1u ? (uint8_t)b64_char((w >> 6) & 63u) : (uint8_t)'=';
+            q[3] = rem > 2u ? (uint8_t)b64_char(w & 63u) : (uint8_t)'=';
+            if ((g & 15u) == 15u || g + 1u == ngroups) q[4] = (uint8_t)'\n';
+        }
+    }
+}
+
+}  // namespace
+
+size_t pem_scan_temp_bytes(uint64_t n_items) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n_items);
+    return bytes;
+}
+
+// sizes -> pem_off[0..n] (exclusive scan, pem_off[n] = total) -> text.  `sizes` is scratch of n+1 words.
+cudaError_t launch_pem_encode(const uint8_t* blob, const uint64_t* offsets, const uint32_t* lens, const uint8_t* select, uint64_t n,
+                              uint64_t* sizes, void* scan_temp, size_t scan_temp_bytes, uint64_t* pem_off, uint8_t* pem, uint64_t cap,
+                              int* error_flag, int sm_count, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    pem_sizes_kernel<<<(unsigned)((n + 256) / 256), 256, 0, s>>>(offsets, lens, select, n, sizes);
+    cudaError_t err = cub::DeviceScan::ExclusiveSum(scan_temp, scan_temp_bytes, sizes, pem_off, (int)(n + 1), s);
+    if (err != cudaSuccess) return err;
+    pem_encode_kernel<<<grid_for_warps(n, sm_count), 256, 0, s>>>(blob, offsets, lens, select, n, pem_off, pem, cap, error_flag);
+    return cudaGetLastError();
+}
+
+}  // namespace ctmr

@@ -176,6 +176,10 @@ __host__ __device__ __forceinline__ uint64_t issuer_cert_finish(uint64_t acc, ui
     return fe_mix64(acc ^ ((uint64_t)len << 32)) | (1ull << 63);  // never 0
 }
 
+size_t pem_scan_temp_bytes(uint64_t n_items);
+cudaError_t launch_pem_encode(const uint8_t* blob, const uint64_t* offsets, const uint32_t* lens, const uint8_t* select, uint64_t n,
+                              uint64_t* sizes, void* scan_temp, size_t scan_temp_bytes, uint64_t* pem_off, uint8_t* pem, uint64_t cap,
+                              int* error_flag, int sm_count, cudaStream_t s);
 size_t fe_scan_temp_bytes(uint64_t n_items);
 cudaError_t launch_fe_decode(const FeParams& p, void* scan_temp, size_t scan_temp_bytes, int sm_count, cudaStream_t s);
 cudaError_t launch_fe_frame(const FeParams& p, cudaStream_t s);

@@ -41,6 +41,12 @@ class BatchResult:
     crldp_len: np.ndarray | None = None
     first_issuer_dn: np.ndarray | None = None
     first_crldp: np.ndarray | None = None
+    # PEM of the new certificates (want_pem=True): texts back to back, entry i = pem[pem_off[i]:pem_off[i+1]]
+    pem: np.ndarray | None = None
+    pem_off: np.ndarray | None = None
+
+    def pem_of(self, i: int) -> bytes:
+        return self.pem[int(self.pem_off[i]):int(self.pem_off[i + 1])].tobytes()
 
 
 class KnownCertificatesView:
@@ -54,6 +60,13 @@ class KnownCertificatesView:
         d = (C.c_uint8 * 32).from_buffer_copy(self.issuer_digest)
         self._db._check(self._db._lib.ctmr_set_cardinality(self._db._h, self.exp_hour, d, C.byref(out)))
         return out.value
+
+
+def _attach_pem(o: "capi.Out", res: BatchResult, n: int, der_bytes: int):
+    """Room for the PEM of every certificate of the batch (the worst case: all new)."""
+    res.pem = np.zeros(der_bytes // 3 * 4 + der_bytes // 48 + 64 * n + 256, np.uint8)
+    res.pem_off = np.zeros(n + 1, np.uint64)
+    o.pem, o.pem_cap, o.pem_off = capi.ptr(res.pem), res.pem.size, capi.ptr(res.pem_off)
 
 
 class RawBatchResult:
@@ -149,7 +162,8 @@ class GpuCertDatabase:
 
     # ------------------------------------------------------------------ the hot path, host buffers
     def store_batch(self, blob, offsets, issuer_blob, issuer_offsets, issuer_idx, now_unix_ns: int,
-                    want_sha: bool = True, out: BatchResult | None = None, want_meta: bool = False) -> BatchResult:
+                    want_sha: bool = True, out: BatchResult | None = None, want_meta: bool = False,
+                    want_pem: bool = False) -> BatchResult:
         """One batch through ctmr_process_batch (HOST buffers in, HOST buffers out)."""
         blob = np.ascontiguousarray(blob, np.uint8)
         offsets = np.ascontiguousarray(offsets, np.uint64)
@@ -173,6 +187,8 @@ class GpuCertDatabase:
                      capi.ptr(out.first_issuer_hour),
                      *([capi.ptr(out.issuer_name_off), capi.ptr(out.issuer_name_len), capi.ptr(out.crldp_off),
                         capi.ptr(out.crldp_len), capi.ptr(out.first_issuer_dn), capi.ptr(out.first_crldp)] if want_meta else [None] * 6))
+        if want_pem:
+            _attach_pem(o, out, n, int(blob.size))
         self._check(self._lib.ctmr_process_batch(self._h, capi.ptr(blob), capi.ptr(offsets), n,
                                                  capi.ptr(issuer_blob) if n_iss else None,
                                                  capi.ptr(issuer_offsets) if n_iss else None, n_iss,
@@ -181,7 +197,7 @@ class GpuCertDatabase:
 
     # ------------------------------------------------------------------ CT wire-format front end (include/ctmr_frontend.h)
     def store_raw_entries(self, text, leaf_off, leaf_len, extra_off, extra_len, now_unix_ns: int, want_sha: bool = True,
-                          want_meta: bool = False) -> "RawBatchResult":
+                          want_meta: bool = False, want_pem: bool = False) -> "RawBatchResult":
         """get-entries strings (base64 leaf_input / extra_data, spans into `text`) through ctmr_process_raw:
         what GetRawEntries' JSON decode, ct.LogEntryFromLeaf (ct-fetch.go:424,452) and insertCTWorker + Store do."""
         text = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, np.uint8)
@@ -197,6 +213,8 @@ class GpuCertDatabase:
                              capi.ptr(p.first_issuer_dn), capi.ptr(p.first_crldp)] if want_meta else [None] * 6))
         for name in ("entry_status", "entry_type", "timestamp_ms", "issuer", "leaf_src", "leaf_off", "leaf_len"):
             setattr(o, name, capi.ptr(getattr(r, name)))
+        if want_pem:
+            _attach_pem(o.path, p, n, (int(leaf_len.sum()) + int(extra_len.sum())) // 4 * 3)
         b = capi.RawBatch(capi.ptr(text), text.size, capi.ptr(leaf_off), capi.ptr(leaf_len), capi.ptr(extra_off), capi.ptr(extra_len),
                           n, now_unix_ns)
         self._check(self._lib.ctmr_process_raw(self._h, C.byref(b), C.byref(o)))

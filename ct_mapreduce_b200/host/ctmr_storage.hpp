@@ -485,8 +485,13 @@ class GpuCertDatabase {
         std::vector<int64_t> exp_hour(n);
         std::vector<uint32_t> soff(n), slen(n), noff(n), nlen(n), coff(n), clen(n);
         std::vector<uint8_t> first_dn(n), first_crl(n);
+        // PEM of the new certificates comes back encoded by the GPU; room for "all new"
+        const uint64_t der_bytes = n ? offsets[n] - offsets[0] : 0;
+        std::vector<uint8_t> pem(der_bytes / 3 * 4 + der_bytes / 48 + 64 * n + 256);
+        std::vector<uint64_t> pem_off(n + 1);
         ctmr_out out{status.data(), nullptr, exp_hour.data(), soff.data(), slen.data(), unknown.data(), first.data(),
-                     noff.data(), nlen.data(), coff.data(), clen.data(), first_dn.data(), first_crl.data()};
+                     noff.data(), nlen.data(), coff.data(), clen.data(), first_dn.data(), first_crl.data(),
+                     pem.data(), pem.size(), pem_off.data()};
         int rc = ctmr_process_batch(ctx_, blob, offsets, n, issuer_blob, issuer_offsets, n_issuers, issuer_idx, now_unix_ns, &out);
         if (rc != CTMR_OK) return std::string("ctmr_process_batch: ") + ctmr_last_error(ctx_);  // like a Redis outage: the caller stops
         std::vector<uint32_t> dense(n_issuers);
@@ -533,8 +538,9 @@ class GpuCertDatabase {
                     Error e = backend_->AllocateExpDateAndIssuer(expDate, issuer);
                     if (!ok(e)) return e;
                 }
-                Error e = backend_->StoreCertificatePEM(serial, expDate, issuer,
-                                                        PemEncode(blob + offsets[i], (size_t)(offsets[i + 1] - offsets[i])));
+                Error e = backend_->StoreCertificatePEM(
+                    serial, expDate, issuer,
+                    std::string(reinterpret_cast<const char*>(pem.data() + pem_off[i]), (size_t)(pem_off[i + 1] - pem_off[i])));
                 if (!ok(e)) return e;
                 ++st.pem_writes;
             }

@@ -111,13 +111,9 @@ func NewResult(n int) *Result {
 		make([]uint8, n), make([]uint8, n)}
 }
 
-// ProcessBatch = parse + certIsFilteredOut + Store decisions for every entry of the batch.
-// nowUnixNs replaces time.Now() at ct-fetch.go:52.
-func (c *Ctx) ProcessBatch(b *Batch, nowUnixNs int64, r *Result) error {
-	if b.N == 0 {
-		return nil
-	}
-	out := C.ctmr_out{
+// cOut is the ctmr_out pointer table over the Go-owned result arrays (shared with ProcessRaw, frontend.go).
+func (r *Result) cOut() C.ctmr_out {
+	return C.ctmr_out{
 		status:            (*C.uint8_t)(unsafe.Pointer(&r.Status[0])),
 		sha256:            (*C.uint8_t)(unsafe.Pointer(&r.SHA256[0])),
 		exp_hour:          (*C.int64_t)(unsafe.Pointer(&r.ExpHour[0])),
@@ -126,6 +122,15 @@ func (c *Ctx) ProcessBatch(b *Batch, nowUnixNs int64, r *Result) error {
 		was_unknown:       (*C.uint8_t)(unsafe.Pointer(&r.WasUnknown[0])),
 		first_issuer_hour: (*C.uint8_t)(unsafe.Pointer(&r.FirstIssuerHour[0])),
 	}
+}
+
+// ProcessBatch = parse + certIsFilteredOut + Store decisions for every entry of the batch.
+// nowUnixNs replaces time.Now() at ct-fetch.go:52.
+func (c *Ctx) ProcessBatch(b *Batch, nowUnixNs int64, r *Result) error {
+	if b.N == 0 {
+		return nil
+	}
+	out := r.cOut()
 	var ib *C.uint8_t
 	var io *C.uint64_t
 	if len(b.IssuerOffs) > 1 {

@@ -103,6 +103,12 @@ typedef struct ctmr_out {
     uint32_t* crldp_len;
     uint8_t* first_issuer_dn;   /* 1 iff was_unknown and no earlier new certificate of this issuer had the same Name bytes */
     uint8_t* first_crldp;       /* 1 iff was_unknown, extension present, and its bytes are new for this issuer */
+    /* PEM of the NEW certificates, encoded on the device: what Store hands to
+     * StorageBackend.StoreCertificatePEM (storage/filesystemdatabase.go:171-175,197-198), i.e.
+     * pem.EncodeToMemory(&pem.Block{Type: "CERTIFICATE", Bytes: cert.Raw}).  Optional as a group. */
+    uint8_t* pem;               /* [pem_cap] texts of the entries with was_unknown == 1, back to back in entry order */
+    uint64_t pem_cap;           /* too small => CTMR_E_BATCH_TOO_LARGE */
+    uint64_t* pem_off;          /* [n+1]: entry i's text = pem[pem_off[i] .. pem_off[i+1]), empty unless new */
 } ctmr_out;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */

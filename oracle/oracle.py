@@ -389,4 +389,5 @@ def raw_process(db: "DB", text: bytes, leaf_off, leaf_len, extra_off, extra_len,
     ioffs[1:] = np.cumsum([len(x) for x in issuers], dtype=np.uint64)
     iblob = np.frombuffer(b"".join(issuers) or b"\0", np.uint8)
     r.path = db.process(blob, offsets, iblob, ioffs, issuer_idx, now_ns)
+    r.leaves = leaves  # the DER each entry's certificate was taken from (b"" for dropped entries)
     return r

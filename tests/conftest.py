@@ -40,6 +40,14 @@ def ora():
     return oracle
 
 
+def go_pem(der: bytes) -> bytes:
+    """encoding/pem.EncodeToMemory(&pem.Block{Type: "CERTIFICATE", Bytes: der}) -- what FilesystemDatabase.Store
+    passes to StoreCertificatePEM (storage/filesystemdatabase.go:171-175,197-198): 64-character lines."""
+    b = base64.b64encode(der)
+    lines = b"".join(b[i:i + 64] + b"\n" for i in range(0, len(b), 64))
+    return b"-----BEGIN CERTIFICATE-----\n" + lines + b"-----END CERTIFICATE-----\n"
+
+
 def pack(ders):
     """list of bytes -> (blob u8, offsets u64)"""
     offsets = np.zeros(len(ders) + 1, np.uint64)

@@ -175,6 +175,20 @@ def test_front_end_and_leaf_api_share_one_known_set(eng, ora):
         assert np.array_equal(r2.timestamp_ms, TS0 + np.arange(n, dtype=np.uint64))
 
 
+def test_pem_of_new_certificates_from_raw_pages(eng, ora):
+    """The decoded DER exists only in HBM: its PEM (Store's argument to StoreCertificatePEM) comes back for NEW certificates."""
+    from conftest import go_pem
+    n = 4000
+    text, lo, ll, xo, xl, _ = synth_pages(ora, n, seed=5, dup_mode=1)
+    odb = ora.DB(b"", True)
+    r_o = ora.raw_process(odb, text, lo, ll, xo, xl, NOW_NS)
+    with eng.GpuCertDatabase(log_expired_entries=True, table_capacity=1 << 16, max_batch_entries=900) as db:
+        r_g = db.store_raw_entries(text, lo, ll, xo, xl, NOW_NS, want_pem=True)
+    assert np.array_equal(r_g.path.was_unknown, r_o.path.was_unknown) and 0 < int(r_o.path.was_unknown.sum()) < n
+    for i in range(n):
+        assert r_g.path.pem_of(i) == (go_pem(r_o.leaves[i]) if r_o.path.was_unknown[i] else b""), i
+
+
 def test_empty_and_tiny_batches(eng, ora):
     from ct_mapreduce_b200 import frontend as fe
     with eng.GpuCertDatabase(table_capacity=1 << 12) as db:

@@ -444,3 +444,35 @@ def test_large_certificates_three_byte_lengths(eng, ora):
         assert_same(r_gpu, r_ora, sha=(flags == 0))
         assert {k: v for k, v in counts.items() if v} == odb.issuer_counts()
     assert int((r_ora.status == 0).sum()) > 20
+
+
+def test_pem_of_new_certificates(eng, ora):
+    """the PEM text Store hands to StoreCertificatePEM, encoded on the device for NEW certificates only."""
+    import ssl
+    from conftest import go_pem
+    from ct_mapreduce_b200 import capi
+    n = 5000
+    cfg = ora.synth_cfg(n, len_mode=1, len_lo=300, len_hi=5000, dup_mode=1)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    der = lambda i: blob[int(offs[i]):int(offs[i + 1])].tobytes()
+    assert go_pem(der(0)).decode() == ssl.DER_cert_to_PEM_cert(der(0))  # the expectation itself, against an independent encoder
+    with eng.GpuCertDatabase(log_expired_entries=True, table_capacity=1 << 16, max_batch_entries=700) as db:  # 8 pipeline slices
+        r = db.store_batch(blob, offs, iblob, ioffs, idx, NOW_NS, want_pem=True)
+        assert 0 < int(r.was_unknown.sum()) < n
+        assert int(r.pem_off[n]) == sum(len(go_pem(der(i))) for i in np.nonzero(r.was_unknown)[0])
+        for i in range(n):
+            assert r.pem_of(i) == (go_pem(der(i)) if r.was_unknown[i] else b""), i
+        # every length residue mod 3 and mod 48 occurs in the corpus
+        lens = np.diff(offs.astype(np.int64))[r.was_unknown == 1]
+        assert set((lens % 3).tolist()) == {0, 1, 2} and len(set((lens % 48).tolist())) == 48
+    with eng.GpuCertDatabase(log_expired_entries=True, table_capacity=1 << 16) as db:
+        out = eng.BatchResult(np.zeros(n, np.uint8), np.zeros((n, 32), np.uint8), np.zeros(n, np.int64), np.zeros(n, np.uint32),
+                              np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.uint8))
+        out.pem, out.pem_off = np.zeros(1000, np.uint8), np.zeros(n + 1, np.uint64)
+        o = capi.Out(*[capi.ptr(getattr(out, f)) for f in ("status", "sha256", "exp_hour", "serial_off", "serial_len", "was_unknown", "first_issuer_hour")],
+                     *([None] * 6), capi.ptr(out.pem), out.pem.size, capi.ptr(out.pem_off))
+        import ctypes as C
+        rc = db._lib.ctmr_process_batch(db._h, capi.ptr(blob), capi.ptr(offs), n, capi.ptr(iblob), capi.ptr(ioffs), ioffs.size - 1,
+                                        capi.ptr(idx), NOW_NS, C.byref(o))
+        assert rc == capi.E_BATCH_TOO_LARGE

@@ -1,0 +1,90 @@
+"""Throughput of the CT wire-format front end (ctmr_process_raw) on one GPU.
+
+    python tools/bench_frontend.py [--entries 200000] [--steps 5] [--warmup 2]
+
+Synthesises get-entries pages (2/3 x509 entries, 1/3 precert entries, chains of one or two certificates) around
+the synthetic corpus, keeps the text in pinned host memory, and times whole ctmr_process_raw calls (host text in,
+host results out).  Prints one JSON line: end-to-end entries/s, and the library's own CUDA-event split of a call
+into front-end kernels (base64, framing, Chain[0] identification) and the map/reduce path behind them.
+"""
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ct_mapreduce_b200 import capi, engine, frontend as fe  # noqa: E402
+
+NOW_NS = 1767225600 * 10**9
+
+
+def make_pages(n, page=1000):
+    cfg = capi.synth_cfg(n)
+    import torch
+    dev = torch.device("cuda:0")
+    blob, offs, idx, total = engine.synth_corpus_device(cfg, 0, n, dev)
+    blob, offs, idx = blob.cpu().numpy(), offs.cpu().numpy(), idx.cpu().numpy()
+    iblob, ioffs = engine.synth_issuers(cfg)
+    issuers = [iblob[int(ioffs[k]):int(ioffs[k + 1])].tobytes() for k in range(ioffs.size - 1)]
+    ikh = [hashlib.sha256(c).digest() for c in issuers]
+    entries = []
+    for i in range(n):
+        leaf = blob[int(offs[i]):int(offs[i + 1])].tobytes()
+        k = int(idx[i])
+        chain = [issuers[k], issuers[(k + 1) % len(issuers)]][: 1 + i % 2]
+        if i % 3 == 0:
+            entries.append((fe.merkle_tree_leaf_precert(1_690_000_000_000 + i, ikh[k], fe.tbs_of(leaf)), fe.precert_chain_entry(leaf, chain)))
+        else:
+            entries.append((fe.merkle_tree_leaf_x509(1_690_000_000_000 + i, leaf), fe.certificate_chain(chain)))
+    bodies = [fe.get_entries_body(entries[a:a + page]) for a in range(0, n, page)]
+    spans, base = [], 0
+    for bd in bodies:
+        spans.append(fe.find_entry_spans(bd, base))
+        base += len(bd)
+    lo, ll, xo, xl = (np.concatenate([s[j] for s in spans]) for j in range(4))
+    return b"".join(bodies), lo, ll, xo, xl, int(total)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--entries", type=int, default=200000)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    a = ap.parse_args()
+    t0 = time.time()
+    text, lo, ll, xo, xl, leaf_bytes = make_pages(a.entries)
+    gen_s = time.time() - t0
+    pin = capi.PinnedBuffer(len(text))
+    pin.view()[:] = np.frombuffer(text, np.uint8)
+    tv = pin.view()
+    chars = int(ll.sum()) + int(xl.sum())
+    with engine.GpuCertDatabase(log_expired_entries=True, table_capacity=1 << 22) as db:
+        fe_ms = path_ms = 0.0
+        for it in range(a.warmup + a.steps):
+            if it == a.warmup:
+                t0 = time.perf_counter()
+            r = db.store_raw_entries(tv, lo, ll, xo, xl, NOW_NS)
+            if it >= a.warmup:
+                f, p, launches = db.frontend_profile_last()
+                fe_ms += f
+                path_ms += p
+        dt = (time.perf_counter() - t0) / a.steps
+        ok = int((r.entry_status == 0).sum())
+    assert ok == a.entries, (ok, a.entries)
+    print(json.dumps({
+        "metric": "ct_raw_entries_per_sec", "value": a.entries / dt, "unit": "entries/s", "entries": a.entries, "steps": a.steps,
+        "ms_per_call": dt * 1e3, "text_bytes": len(text), "base64_chars": chars, "leaf_der_bytes": leaf_bytes,
+        "h2d_gbs": len(text) / dt / 1e9,
+        "frontend_kernels_ms": fe_ms / a.steps, "frontend_kernels_chars_gbs": chars / (fe_ms / a.steps) / 1e6,
+        "frontend_kernels_entries_per_sec": a.entries / (fe_ms / a.steps) * 1e3,
+        "path_ms": path_ms / a.steps, "frontend_launches": launches, "page_synthesis_s": gen_s,
+        "note": "value = whole ctmr_process_raw calls, pinned host text in, host results out, synchronous chunks",
+    }))
+
+
+if __name__ == "__main__":
+    main()
