@@ -19,8 +19,11 @@ ST_COUNT = 8
 ISSUER_NONE = 0xFFFFFFFF
 ISSUER_BAD = 0xFFFFFFFE
 F_NO_FINGERPRINT = 1
+E_INVALID = -1
 E_TABLE_FULL = -4
+E_TOO_MANY_ISSUERS = -5
 E_NO_DEVICE = -6
+E_BATCH_TOO_LARGE = -7
 
 EXPORTS = [
     "ctmr_abi_version", "ctmr_create", "ctmr_destroy", "ctmr_last_error", "ctmr_host_alloc", "ctmr_host_free",
