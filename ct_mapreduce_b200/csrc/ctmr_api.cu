@@ -1218,6 +1218,32 @@ int ctmr_table_stats(ctmr_ctx* c, uint64_t* used, uint64_t* capacity) {
     return CTMR_OK;
 }
 
+// Redis TTLs firing: every set "serials::<expDate>::<issuer>" carries EXPIREAT(expDate)
+// (storage/knowncertificates.go:44-47,98-104), so at `now` the sets with expDate <= now no longer exist.
+int ctmr_evict_expired(ctmr_ctx* c, int64_t now_unix_sec, uint64_t* evicted_out) {
+    if (!c) return CTMR_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    unsigned long long counters[2] = {0, 0};
+    unsigned long long* dev = c->small_dev + 92;  // [92] live, [93] expired, [94] compaction cursor
+    CU(c, cudaMemsetAsync(dev, 0, 3 * sizeof(unsigned long long), c->stream));
+    CU(c, launch_evict_count(c->st, now_unix_sec, dev, c->stream));
+    CU(c, cudaMemcpyAsync(counters, dev, sizeof counters, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (evicted_out) *evicted_out = counters[1];
+    if (counters[1] == 0) return CTMR_OK;
+    // open addressing with linear probing: taking slots out would cut probe chains, so the survivors are
+    // compacted aside, the table is cleared and they are inserted again (first-seen indices preserved)
+    KnownSlot* keep = nullptr;
+    if (counters[0]) CU(c, cudaMalloc(&keep, counters[0] * sizeof(KnownSlot)));
+    if (counters[0]) CU(c, launch_evict_compact(c->st, now_unix_sec, keep, dev + 2, c->stream));
+    CU(c, cudaMemsetAsync(c->st.table, 0, (c->st.table_mask + 1) * sizeof(KnownSlot), c->stream));
+    CU(c, launch_evict_reinsert(c->st, keep, counters[0], c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(keep);
+    return ctmr_check_device(c, nullptr);
+}
+
 // ------------------------------------------------------------------------------------------------ CT wire-format front end
 // get-entries strings -> decode -> framing -> Chain[0] identification -> the path.
 int ctmr_process_raw(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {

@@ -245,6 +245,64 @@ __global__ void __launch_bounds__(256) table_count_kernel(DeviceState st, unsign
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
 }
 
+// ---- TTL eviction: sets whose EXPIREAT time has passed vanish ---------------------------
+// pass 1: count expired / surviving ready slots, take the expired ones out of the per-issuer histogram
+__global__ void __launch_bounds__(256) evict_count_kernel(DeviceState st, int64_t now_sec, unsigned long long* counters /* [2]: live, expired */) {
+    unsigned int live = 0, dead = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= st.table_mask; i += (uint64_t)gridDim.x * blockDim.x) {
+        const KnownSlot& sl = st.table[i];
+        if ((sl.tag & 3ull) != 2ull) continue;
+        const int64_t hour = (int32_t)sl.body[0];
+        if (hour * 3600 <= now_sec) {
+            ++dead;
+            if (sl.body[1] < st.max_issuers) atomicAdd(st.issuer_counts + sl.body[1], ~0ull);  // -1
+        } else {
+            ++live;
+        }
+    }
+    live = __reduce_add_sync(0xffffffffu, live);
+    dead = __reduce_add_sync(0xffffffffu, dead);
+    if ((threadIdx.x & 31) == 0) {
+        if (live) atomicAdd(counters, (unsigned long long)live);
+        if (dead) atomicAdd(counters + 1, (unsigned long long)dead);
+    }
+}
+
+// pass 2: survivors, compacted (order irrelevant)
+__global__ void __launch_bounds__(256) evict_compact_kernel(DeviceState st, int64_t now_sec, KnownSlot* __restrict__ keep,
+                                                            unsigned long long* cursor) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= st.table_mask; i += (uint64_t)gridDim.x * blockDim.x) {
+        const KnownSlot sl = st.table[i];
+        if ((sl.tag & 3ull) != 2ull) continue;
+        if ((int64_t)(int32_t)sl.body[0] * 3600 <= now_sec) continue;
+        keep[atomicAdd(cursor, 1ull)] = sl;
+    }
+}
+
+// pass 3 (after the table has been cleared): linear probing leaves no holes only if every survivor is re-inserted
+__global__ void __launch_bounds__(256) evict_reinsert_kernel(DeviceState st, const KnownSlot* __restrict__ keep, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t body[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) body[k] = keep[i].body[k];
+    known_insert(st.table, st.table_mask, st.error_flag, body, keep[i].inv_first);
+}
+
+cudaError_t launch_evict_count(const DeviceState& st, int64_t now_sec, unsigned long long* counters, cudaStream_t s) {
+    evict_count_kernel<<<148 * 8, 256, 0, s>>>(st, now_sec, counters);
+    return cudaGetLastError();
+}
+cudaError_t launch_evict_compact(const DeviceState& st, int64_t now_sec, KnownSlot* keep, unsigned long long* cursor, cudaStream_t s) {
+    evict_compact_kernel<<<148 * 8, 256, 0, s>>>(st, now_sec, keep, cursor);
+    return cudaGetLastError();
+}
+cudaError_t launch_evict_reinsert(const DeviceState& st, const KnownSlot* keep, uint64_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    evict_reinsert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st, keep, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_table_count(const DeviceState& st, unsigned long long* out, cudaStream_t s) {
     table_count_kernel<<<148 * 8, 256, 0, s>>>(st, out);
     return cudaGetLastError();

@@ -288,6 +288,13 @@ class GpuCertDatabase:
         snap = np.ascontiguousarray(snap, np.uint8)
         self._check(self._lib.ctmr_snapshot_load(self._h, capi.ptr(snap), snap.size))
 
+    def evict_expired(self, now_unix_sec: int) -> int:
+        """Apply the Redis TTLs (EXPIREAT(expDate) on every serials:: set, knowncertificates.go:98-104): sets with
+        expDate <= now vanish.  Returns the number of serials dropped."""
+        n = C.c_uint64(0)
+        self._check(self._lib.ctmr_evict_expired(self._h, int(now_unix_sec), C.byref(n)))
+        return int(n.value)
+
     # ------------------------------------------------------------------ reducers' read side
     def get_known_certificates(self, exp_hour: int, issuer_digest: bytes) -> KnownCertificatesView:
         return KnownCertificatesView(self, exp_hour, issuer_digest)

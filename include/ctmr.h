@@ -161,6 +161,13 @@ int ctmr_table_stats(ctmr_ctx* ctx, uint64_t* slots_used, uint64_t* capacity);
  * (issuer, expDate) pair counts as already allocated.  HOST buffers. */
 int ctmr_preload_known(ctmr_ctx* ctx, int64_t exp_hour, const uint8_t issuer_digest[32], const uint8_t* serial_blob,
                        const uint64_t* serial_offsets /* [n+1] */, uint64_t n);
+/* Redis TTLs: WasUnknown puts EXPIREAT(expDate) on every "serials::<expDate>::<issuer>" set
+ * (storage/knowncertificates.go:44-47,98-104; expDate = hour-truncated NotAfter, storage/types.go:371-373), so
+ * as time passes whole sets vanish from the reference's state.  This call applies that to the device state:
+ * every set with expDate <= now is dropped (its serials are unknown again, it stops counting towards
+ * ctmr_issuer_counts / ctmr_set_cardinality, its slots are reclaimed).  IssuerMetadata's seenExpDateBefore memo
+ * is process memory in the reference and is kept.  Call it between batches, e.g. once per hour. */
+int ctmr_evict_expired(ctmr_ctx* ctx, int64_t now_unix_sec, uint64_t* evicted_out);
 /* Snapshot of the derived device state (tables, histograms, issuer registry, next entry index) into a
  * caller buffer, and its restoration into a ctx created with the same capacities.  ctmr_snapshot_size
  * gives the bytes needed.  The reference's analogue is the state it keeps in Redis between runs

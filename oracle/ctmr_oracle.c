@@ -777,6 +777,42 @@ uint64_t ora_db_set_cardinality(ora_db* db, int64_t exp_hour, const uint8_t dige
     return ora_cache_set_cardinality(db->cache, key, kl);
 }
 
+/* What Redis does to the reference's state as time passes: KnownCertificates.WasUnknown sets EXPIREAT(key,
+ * expDate) on "serials::<expDate>::<issuer>" (storage/knowncertificates.go:44-47,98-104; expDate = the
+ * hour-truncated NotAfter, storage/types.go:371-373), so at time `now` every set with expDate <= now is gone:
+ * its members are unknown again and it no longer counts.  IssuerMetadata's seenExpDateBefore memo is process
+ * memory, not Redis, and survives.  Returns the number of serials dropped. */
+uint64_t ora_db_evict_expired(ora_db* db, int64_t now_sec) {
+    ora_cache* c = db->cache;
+    uint64_t dropped = 0;
+    bs_map nm;
+    nm.cap = c->members.cap; nm.n = 0;
+    nm.e = (bs_ent*)calloc(nm.cap, sizeof(bs_ent));
+    for (uint64_t i = 0; i < c->members.cap; ++i) {
+        bs_ent* e = &c->members.e[i];
+        if (!e->key) continue;
+        uint32_t kl;
+        memcpy(&kl, e->key, 4);
+        int gone = 0;
+        for (uint64_t m = 0; m < db->n_metas && !gone; ++m)
+            if (db->metas[m].exp_hour * 3600 <= now_sec && db->metas[m].key_len == kl && memcmp(db->metas[m].key, e->key + 4, kl) == 0) gone = 1;
+        if (gone) { free(e->key); dropped++; continue; }
+        uint64_t j = e->h & (nm.cap - 1);
+        while (nm.e[j].key) j = (j + 1) & (nm.cap - 1);
+        nm.e[j] = *e;
+        nm.n++;
+    }
+    free(c->members.e);
+    c->members = nm;
+    for (uint64_t m = 0; m < db->n_metas; ++m)
+        if (db->metas[m].exp_hour * 3600 <= now_sec) {
+            uint64_t h = fnv1a((const uint8_t*)db->metas[m].key, db->metas[m].key_len);
+            bs_ent* s = bs_find(&c->sets, (const uint8_t*)db->metas[m].key, db->metas[m].key_len, h);
+            if (s->key) s->val = 0; /* SCARD of a missing key is 0 */
+        }
+    return dropped;
+}
+
 void ora_db_filter_counters(ora_db* db, uint64_t out[8]) { memcpy(out, db->counters, sizeof db->counters); }
 
 /* ------------------------------------------------------------------ synthetic corpus on the CPU */

@@ -116,6 +116,7 @@ int ora_db_process(ora_db*, const uint8_t* blob, const uint64_t* offsets, uint64
 uint64_t ora_db_issuer_counts(ora_db*, uint8_t* ids32, uint64_t* counts, uint64_t cap);
 uint64_t ora_db_set_cardinality(ora_db*, int64_t exp_hour, const uint8_t issuer_digest[32]);
 void ora_db_filter_counters(ora_db*, uint64_t out[8]); /* indexed by status code */
+uint64_t ora_db_evict_expired(ora_db*, int64_t now_unix_sec); /* Redis TTLs firing: sets with expDate <= now vanish */
 
 /* timed CPU arm: map-only over a batch (parse + filter + both SHA-256), returns entries kept */
 uint64_t ora_map_only(const uint8_t* blob, const uint64_t* offsets, uint64_t n, const uint8_t* filter,

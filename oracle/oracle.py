@@ -99,6 +99,7 @@ def lib():
         L.ora_db_issuer_counts.argtypes = [vp, vp, vp, u64]; L.ora_db_issuer_counts.restype = u64
         L.ora_db_set_cardinality.argtypes = [vp, i64, vp]; L.ora_db_set_cardinality.restype = u64
         L.ora_db_filter_counters.argtypes = [vp, vp]
+        L.ora_db_evict_expired.argtypes = [vp, i64]; L.ora_db_evict_expired.restype = u64
         L.ora_map_only.argtypes = [vp, vp, u64, vp, sz, C.c_int, i64, C.c_int, vp]; L.ora_map_only.restype = u64
         L.ora_parse_tbs.argtypes = [vp, sz, C.POINTER(OraCert)]; L.ora_parse_tbs.restype = C.c_int
         L.ora_b64_decode.argtypes = [vp, sz, vp, sz]; L.ora_b64_decode.restype = C.c_long
@@ -273,6 +274,10 @@ class DB:
     def set_cardinality(self, hour: int, digest: bytes) -> int:
         d = (C.c_uint8 * 32).from_buffer_copy(digest)
         return lib().ora_db_set_cardinality(self.h, hour, d)
+
+    def evict_expired(self, now_sec: int) -> int:
+        """Redis EXPIREAT firing on every serials:: set whose expDate <= now (knowncertificates.go:98-104)."""
+        return int(lib().ora_db_evict_expired(self.h, now_sec))
 
     def filter_counters(self):
         out = np.zeros(8, np.uint64)

@@ -476,3 +476,35 @@ def test_pem_of_new_certificates(eng, ora):
         rc = db._lib.ctmr_process_batch(db._h, capi.ptr(blob), capi.ptr(offs), n, capi.ptr(iblob), capi.ptr(ioffs), ioffs.size - 1,
                                         capi.ptr(idx), NOW_NS, C.byref(o))
         assert rc == capi.E_BATCH_TOO_LARGE
+
+
+def test_ttl_eviction_matches_redis_expiry(eng, ora):
+    """the reference's sets carry EXPIREAT(expDate); when the TTLs fire, whole sets vanish.  The device
+    state follows: evicted serials are unknown again, counts drop, slots are reclaimed, later batches agree with the oracle."""
+    n = 8000
+    cfg = ora.synth_cfg(n, dup_mode=1)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    odb = ora.DB(b"", True)
+    with eng.GpuCertDatabase(log_expired_entries=True, table_capacity=1 << 15) as db:
+        half = n // 2
+        r_o = odb.process(blob, offs[:half + 1], iblob, ioffs, idx[:half], NOW_NS)
+        r_g = db.store_batch(blob, offs[:half + 1], iblob, ioffs, idx[:half], NOW_NS)
+        assert_same(r_g, r_o)
+        hours = np.sort(r_o.exp_hour[r_o.status == 0])
+        used0 = db.table_stats()[0]
+        assert db.evict_expired(int(hours[0]) * 3600 - 1) == odb.evict_expired(int(hours[0]) * 3600 - 1) == 0   # nothing is due yet
+        cut = int(hours[hours.size // 2]) * 3600          # a set expiring exactly now is gone (EXPIREAT fires at >=)
+        dropped = odb.evict_expired(cut)
+        assert db.evict_expired(cut) == dropped and 0 < dropped < used0
+        assert db.table_stats()[0] == used0 - dropped
+        assert {k: v for k, v in db.issuer_counts().items() if v} == {k: v for k, v in odb.issuer_counts().items() if v}
+        # the second half repeats certificates of the first: the evicted ones are new again, the others still known
+        r_o2 = odb.process(blob, offs[half:], iblob, ioffs, idx[half:], NOW_NS)
+        r_g2 = db.store_batch(blob, offs[half:], iblob, ioffs, idx[half:], NOW_NS)
+        assert_same(r_g2, r_o2)
+        assert 0 < int(r_o2.was_unknown.sum()) < int((r_o2.status == 0).sum())
+        assert {k: v for k, v in db.issuer_counts().items() if v} == {k: v for k, v in odb.issuer_counts().items() if v}
+        # everything is past its TTL eventually
+        assert db.evict_expired(1 << 40) == odb.evict_expired(1 << 40) > 0
+        assert db.table_stats()[0] == 0 and not any(db.issuer_counts().values())
