@@ -136,6 +136,20 @@ class RemoteCache {  // storage/types.go:83-102 -- method set unchanged; channel
     virtual std::pair<CertificateLog, Error> LoadLogState(const std::string& url) = 0;
 };
 
+// Optional extension of a RemoteCache: the SADD / EXPIREAT traffic of one GPU batch in ONE pipelined
+// round trip each (go-redis Pipeline over rediscache.go:57-65,116-120) instead of one per new certificate.  The Go
+// shim discovers it with a type assertion (`if bc, ok := cache.(BatchRemoteCache); ok { ... }`), this mirror with
+// dynamic_cast; a cache without it gets the per-entry calls, so the interface of storage/types.go:83-102 is untouched.
+class BatchRemoteCache {
+  public:
+    virtual ~BatchRemoteCache() = default;
+    struct Insert { std::string key, entry; };
+    struct Expire { std::string key; int64_t unix_time; };
+    // results[i] = what SetInsert(ops[i].key, ops[i].entry) returns when the operations are applied in order
+    virtual std::pair<std::vector<bool>, Error> SetInsertBatch(const std::vector<Insert>& ops) = 0;
+    virtual Error ExpireAtBatch(const std::vector<Expire>& ops) = 0;
+};
+
 class StorageBackend {  // storage/types.go:46-68 -- method set unchanged (context.Context dropped)
   public:
     virtual ~StorageBackend() = default;
@@ -217,6 +231,30 @@ class MockRemoteCache : public RemoteCache {  // storage/mockcache.go
     std::map<std::string, CertificateLog> logs_;
 };
 
+// MockRemoteCache that also offers the pipelined extension; round_trips counts what a Redis would have seen
+class MockBatchRemoteCache : public MockRemoteCache, public BatchRemoteCache {
+  public:
+    uint64_t round_trips = 0;
+    std::pair<std::vector<bool>, Error> SetInsertBatch(const std::vector<Insert>& ops) override {
+        ++round_trips;
+        std::vector<bool> r(ops.size());
+        for (size_t i = 0; i < ops.size(); ++i) {
+            auto one = MockRemoteCache::SetInsert(ops[i].key, ops[i].entry);
+            if (!ok(one.second)) return {r, one.second};
+            r[i] = one.first;
+        }
+        return {r, ""};
+    }
+    Error ExpireAtBatch(const std::vector<Expire>& ops) override {
+        ++round_trips;
+        for (const auto& o : ops) {
+            Error e = MockRemoteCache::ExpireAt(o.key, o.unix_time);
+            if (!ok(e)) return e;
+        }
+        return "";
+    }
+};
+
 class NoopBackend : public StorageBackend {  // storage/noopbackend.go: stores succeed, loads error
   public:
     Error MarkDirty(const std::string&) override { return ""; }
@@ -272,6 +310,8 @@ class KnownCertificates {  // storage/knowncertificates.go
         return out;
     }
     void MarkExpirySet() { expirySet_ = true; }
+    bool ExpirySet() const { return expirySet_; }
+    int64_t ExpireTimeUnix() const { return expDate_.ExpireTimeUnix(); }
 
   private:
     ExpDate expDate_;
@@ -502,6 +542,32 @@ class GpuCertDatabase {
         std::set<std::string> dirty_days;
         BatchStats st;
         st.entries = n;
+        // A cache with the pipelined extension gets this batch's SADDs and EXPIREATs in one round trip each
+        BatchRemoteCache* pipelined = dynamic_cast<BatchRemoteCache*>(cache_);
+        if (pipelined) {
+            std::vector<BatchRemoteCache::Insert> inserts;
+            std::vector<BatchRemoteCache::Expire> expires;
+            for (uint64_t i = 0; i < n; ++i) {
+                if (status[i] != CTMR_ST_OK || !unknown[i]) continue;
+                uint8_t dig[32];
+                ctmr_issuer_digest(ctx_, dense[issuer_idx[i]], dig);
+                KnownCertificates* kc = GetKnownCertificates(ExpDate{exp_hour[i]}, Issuer::FromDigest(dig));
+                inserts.push_back({kc->serialId(), Serial::FromBytes(blob + offsets[i] + soff[i], slen[i]).BinaryString()});
+                if (!kc->ExpirySet()) {  // knowncertificates.go:44-47: once per KnownCertificates object
+                    expires.push_back({kc->serialId(), kc->ExpireTimeUnix()});
+                    kc->MarkExpirySet();
+                }
+            }
+            if (!inserts.empty()) {
+                auto r = pipelined->SetInsertBatch(inserts);
+                if (!ok(r.second)) return r.second;
+                st.cache_inserts += inserts.size();
+            }
+            if (!expires.empty()) {
+                Error e = pipelined->ExpireAtBatch(expires);
+                if (!ok(e)) return e;
+            }
+        }
         for (uint64_t i = 0; i < n; ++i) {
             st.status[status[i] < CTMR_ST__COUNT ? status[i] : CTMR_ST_PARSE_ERR]++;
             if (status[i] != CTMR_ST_OK) continue;  // the reference logs and continues (ct-fetch.go:206-232)
@@ -513,10 +579,12 @@ class GpuCertDatabase {
             if (unknown[i]) {
                 ++st.unknown;
                 const Serial serial = Serial::FromBytes(blob + offsets[i] + soff[i], slen[i]);
-                KnownCertificates* kc = GetKnownCertificates(expDate, issuer);
-                auto r = kc->WasUnknown(serial);  // SADD only for entries the GPU found new
-                ++st.cache_inserts;
-                if (!ok(r.second)) return r.second;
+                if (!pipelined) {
+                    KnownCertificates* kc = GetKnownCertificates(expDate, issuer);
+                    auto r = kc->WasUnknown(serial);  // SADD only for entries the GPU found new
+                    ++st.cache_inserts;
+                    if (!ok(r.second)) return r.second;
+                }
                 // IssuerMetadata.Accumulate: the GPU says which new certificates carry a Name / CRL-DP value not
                 // seen before for this issuer; only those are formatted / parsed (its own memo stays authoritative)
                 IssuerMetadata* im = GetIssuerMetadata(issuer);

@@ -122,7 +122,7 @@ static std::string hex(const std::string& s) {
     return o;
 }
 
-static int run_gpu(const std::string& dir, int batches) {
+static int run_gpu(const std::string& dir, int batches, bool pipelined) {
     auto blob = read_all<uint8_t>(dir + "/blob.bin");
     auto offs = read_all<uint64_t>(dir + "/offsets.bin");
     auto iblob = read_all<uint8_t>(dir + "/issuer_blob.bin");
@@ -138,7 +138,9 @@ static int run_gpu(const std::string& dir, int batches) {
     cfg.issuer_cn_filter_len = (uint32_t)filt.size();
     ctmr_ctx* ctx = nullptr;
     if (ctmr_create(&cfg, &ctx) != CTMR_OK) { std::fprintf(stderr, "ctmr_create: %s\n", ctmr_last_error(nullptr)); return 3; }
-    MockRemoteCache cache;
+    MockBatchRemoteCache batch_cache;  // offers SetInsertBatch / ExpireAtBatch (found by dynamic_cast in StoreBatch)
+    MockRemoteCache plain_cache;
+    MockRemoteCache& cache = pipelined ? static_cast<MockRemoteCache&>(batch_cache) : plain_cache;
     MockBackend backend;
     GpuCertDatabase db(ctx, &cache, &backend);
     BatchStats total{};
@@ -155,7 +157,7 @@ static int run_gpu(const std::string& dir, int batches) {
     std::ofstream out(dir + "/state.txt");
     out << "STATS entries " << total.entries << " stored " << total.stored << " unknown " << total.unknown << " set_insert_calls "
         << cache.set_insert_calls << " pem_writes " << total.pem_writes << " mark_dirty_calls " << backend.mark_dirty_calls
-        << " dn_formats " << total.dn_formats << " crl_parses " << total.crl_parses << "\n";
+        << " dn_formats " << total.dn_formats << " crl_parses " << total.crl_parses << " round_trips " << batch_cache.round_trips << "\n";
     for (const auto& kv : cache.Data)
         for (const auto& m : kv.second) out << "SET " << kv.first << " " << hex(m) << "\n";
     // issuer:: and crl:: members are text: also dump them readable (spaces escaped) for the pytest side
@@ -215,7 +217,8 @@ int main(int argc, char** argv) {
         std::puts("host cpu tests: 7 passed");
         return 0;
     }
-    if (argc >= 4 && std::string(argv[1]) == "gpu") return run_gpu(argv[2], std::atoi(argv[3]));
+    if (argc >= 4 && std::string(argv[1]) == "gpu")
+        return run_gpu(argv[2], std::atoi(argv[3]), argc >= 5 && std::string(argv[4]) == "pipelined");
     std::fprintf(stderr, "usage: host_tests cpu | gpu <dir> <batches>\n");
     return 64;
 }

@@ -33,7 +33,8 @@ def test_reference_reducer_tests_on_cpp_host(host_bin):
 
 
 @pytest.mark.gpu
-def test_store_batch_drives_remote_cache_like_the_reference(host_bin, ora, tmp_path):
+@pytest.mark.parametrize("mode", ["per_entry", "pipelined"])
+def test_store_batch_drives_remote_cache_like_the_reference(host_bin, ora, tmp_path, mode):
     n = 6000
     cfg = ora.synth_cfg(n, len_mode=1, len_lo=512, len_hi=4096, dup_mode=1)
     blob, offs, idx = ora.synth_corpus(cfg, 0, n)
@@ -43,7 +44,9 @@ def test_store_batch_drives_remote_cache_like_the_reference(host_bin, ora, tmp_p
     for name, arr in (("blob", blob), ("offsets", offs), ("issuer_blob", iblob), ("issuer_offsets", ioffs), ("issuer_idx", idx),
                       ("now_ns", np.array([NOW_NS], np.int64)), ("filter", np.frombuffer(README_FILTER, np.uint8))):
         np.ascontiguousarray(arr).tofile(tmp_path / f"{name}.bin")
-    r = subprocess.run([host_bin, "gpu", str(tmp_path), "3"], capture_output=True, text=True)
+    # "pipelined": the cache also implements BatchRemoteCache (SetInsertBatch / ExpireAtBatch): same final state,
+    # but the serial inserts and expiries of a batch travel in one round trip each
+    r = subprocess.run([host_bin, "gpu", str(tmp_path), "3"] + (["pipelined"] if mode == "pipelined" else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
 
     # what the reference would have left behind (sequential Store semantics from the oracle)
@@ -119,5 +122,6 @@ def test_store_batch_drives_remote_cache_like_the_reference(host_bin, ora, tmp_p
     n_issuers_seen = len({int(idx[i]) for i in np.nonzero(want.was_unknown)[0]})
     assert stats["set_insert_calls"] == n_unknown + len(exp_str) < stats["stored"]  # + one per distinct DN / CRL string
     assert stats["pem_writes"] == n_unknown
+    assert stats["round_trips"] == (2 * 3 if mode == "pipelined" else 0)  # 3 batches x (one SADD pipeline + one EXPIREAT pipeline)
     # the GPU's first-seen bits keep the host's string work at O(issuers), not O(new certificates)
     assert stats["dn_formats"] == n_issuers_seen and stats["crl_parses"] <= 2 * n_issuers_seen < n_unknown
