@@ -246,7 +246,9 @@ def main():
     stream_a = torch.cuda.Stream(dev)    # A: K_map
     torch.cuda.synchronize(dev)
     torch.cuda.set_stream(stream)
-    NSUB = 4 if (world > 1 and n >= (1 << 21)) else 1  # overlap hides the exchange at N>1; at N=1 map and reduce contend for the same SMs (measured: no gain)
+    # overlap hides the exchange at N>1 (only the LAST sub-batch's reduce chain is exposed, so more, smaller
+    # sub-batches shorten the step until launch overheads win); at N=1 the library pipelines internally
+    NSUB = int(os.environ.get("CTMR_BENCH_NSUB", "4")) if (world > 1 and n >= (1 << 21)) else 1
     bounds = [n * k // NSUB for k in range(NSUB + 1)]
 
     step_no = [0]
