@@ -172,3 +172,82 @@ def test_raw_process_composes_the_sequential_semantics(ora, certs, golden):
     assert r.path.status.tolist() == [0, 0, 5, 1]           # OK, OK, NO_ISSUER, PARSE_ERR (dropped)
     assert r.path.was_unknown.tolist() == [1, 0, 0, 0]
     assert r.timestamp_ms.tolist() == [TS, TS + 1, TS + 2, TS + 3]
+
+
+# ---- the framing rules once more, independently (plain Python over RFC 6962), against generated structures ----
+
+def _py_entry_from_leaf(li: bytes, ed: bytes):
+    """RFC 6962 §3.4 / §4.6 read straight off the RFC with struct -- no code shared with the C oracle.
+    Returns (status, entry_type, leaf bytes or None, chain list or None); the certificate parses are left out
+    (status is what LogEntryFromLeaf's tls.Unmarshal calls decide)."""
+    def opaque24(buf, at, lo=1):
+        if at + 3 > len(buf):
+            raise ValueError
+        n = int.from_bytes(buf[at:at + 3], "big")
+        if n < lo or at + 3 + n > len(buf):
+            raise ValueError
+        return buf[at + 3:at + 3 + n], at + 3 + n
+
+    def chain_at(buf, at):
+        body, end = opaque24(buf, at, lo=0)
+        if end != len(buf):
+            raise ValueError
+        out, q = [], 0
+        while q < len(body):
+            c, q = opaque24(body, q)
+            out.append(c)
+        return out
+
+    if len(li) < 12 or li[1] != 0:
+        return 2, 0xFF, None, None
+    etype = struct.unpack(">H", li[10:12])[0]
+    if etype not in (0, 1):
+        return 3, 0xFF, None, None
+    try:
+        at = 12 + (32 if etype == 1 else 0)
+        body, at = opaque24(li, at)
+        if at + 2 > len(li) or at + 2 + struct.unpack(">H", li[at:at + 2])[0] != len(li):
+            raise ValueError
+    except ValueError:
+        return 2, etype, None, None
+    try:
+        if etype == 0:
+            return 0, 0, body, chain_at(ed, 0)
+        pre, at = opaque24(ed, 0)
+        return 0, 1, pre, chain_at(ed, at)
+    except ValueError:
+        return 4, etype, None, None
+
+
+_blob = st.binary(min_size=1, max_size=40)
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.booleans(), st.integers(0, 2**64 - 1), _blob, st.lists(_blob, max_size=4), st.binary(max_size=6),
+       st.sampled_from(["ok", "trunc_li", "trunc_ed", "extra_li", "extra_ed", "flip_li", "flip_ed", "type", "leaftype"]),
+       st.integers(0, 10**6))
+def test_framing_agrees_with_an_independent_reading_of_rfc6962(ora, precert, ts, cert, chain, ext, how, where):
+    li = fe.merkle_tree_leaf_precert(ts, bytes(32), cert, ext) if precert else fe.merkle_tree_leaf_x509(ts, cert, ext)
+    ed = fe.precert_chain_entry(cert, chain) if precert else fe.certificate_chain(chain)
+    li, ed = bytearray(li), bytearray(ed)
+    if how == "trunc_li": del li[where % len(li):]
+    elif how == "trunc_ed": del ed[where % len(ed):]
+    elif how == "extra_li": li += b"\x00" * (1 + where % 3)
+    elif how == "extra_ed": ed += b"\x00" * (1 + where % 3)
+    elif how == "flip_li": li[where % len(li)] ^= 1 << (where % 8)
+    elif how == "flip_ed": ed[where % len(ed)] ^= 1 << (where % 8)
+    elif how == "type": li[10:12] = struct.pack(">H", where % 65536)
+    elif how == "leaftype": li[1] = where % 256
+    want_st, want_type, want_leaf, want_chain = _py_entry_from_leaf(bytes(li), bytes(ed))
+    got_st, e = ora.entry_from_leaf(bytes(li), bytes(ed))
+    if want_st != 0:
+        assert got_st == want_st
+        return
+    # framing is fine: what is left is the certificate parse of random bytes, which fails (BAD_CERT) unless DER by luck
+    assert got_st in (ora.FE_OK, ora.FE_BAD_CERT)
+    assert e.entry_type == want_type and e.timestamp_ms == struct.unpack(">Q", bytes(li[2:10]))[0]
+    src = ed if e.leaf_src else li
+    assert bytes(src[e.leaf_off:e.leaf_off + e.leaf_len]) == want_leaf
+    assert e.chain_count == len(want_chain)
+    if want_chain:
+        assert bytes(ed[e.chain0_off:e.chain0_off + e.chain0_len]) == want_chain[0]
