@@ -356,6 +356,11 @@ static cudaError_t launch_stream_t(const MapParams& p, int sm_count, int ctas_pe
     if (err != cudaSuccess) return err;
     const uint64_t ngroups = (p.n + 31) / 32;
     uint64_t ctas = (uint64_t)sm_count * ctas_per_sm;
+    // The grid is persistent and fills every SM, so a kernel launched on another stream while K_map runs (the
+    // NCCL key exchange of the previous sub-batch at N>1) finds no free shared memory / registers until K_map
+    // ends.  Leaving a few CTA slots empty gives such kernels somewhere to run.
+    static const int reserve = env_int("CTMR_MAP_RESERVE_CTAS", 0);
+    if (reserve > 0 && (uint64_t)reserve < ctas) ctas -= (uint64_t)reserve;
     const uint64_t need = (ngroups + WARPS - 1) / WARPS;
     if (need < ctas) ctas = need ? need : 1;
     kern<<<(unsigned)ctas, WARPS * 32, Cfg::kSmem, s>>>(p);
