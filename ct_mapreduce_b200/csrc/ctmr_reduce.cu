@@ -342,9 +342,12 @@ __global__ void owner_scan_kernel(const unsigned long long* counts, uint32_t wor
     }
 }
 
+// `limit` = 0: buckets are contiguous (cursors start at the scanned counts).  `limit` > 0: bucket w owns the fixed
+// range [w*limit, (w+1)*limit) (cursors start at w*limit); a record that does not fit raises *overflow and is dropped.
 __global__ void __launch_bounds__(256) owner_scatter_kernel(const ctmr_key* __restrict__ keys, uint64_t n, uint32_t world,
                                                             unsigned long long* __restrict__ cursors,
-                                                            ctmr_key* __restrict__ out, uint32_t* __restrict__ src_pos) {
+                                                            ctmr_key* __restrict__ out, uint32_t* __restrict__ src_pos,
+                                                            uint64_t limit, int* __restrict__ overflow) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
     uint32_t owner = 0;
@@ -363,6 +366,10 @@ __global__ void __launch_bounds__(256) owner_scatter_kernel(const ctmr_key* __re
         if ((threadIdx.x & 31u) == leader) base = atomicAdd(cursors + owner, (unsigned long long)__popc(peers));
         base = __shfl_sync(peers, base, leader);
         const uint64_t dst = base + __popc(peers & ((1u << (threadIdx.x & 31u)) - 1u));
+        if (limit && dst >= (uint64_t)(owner + 1u) * limit) {
+            atomicExch(overflow, 1);
+            return;
+        }
         uint4* o = reinterpret_cast<uint4*>(out + dst);
         o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3;
         src_pos[dst] = (uint32_t)j;
@@ -375,7 +382,22 @@ cudaError_t launch_partition(const ctmr_key* keys, uint64_t n, uint32_t world, c
     if (err != cudaSuccess || !n) return err;
     owner_count_kernel<<<blocks_for(n, 256), 256, 0, s>>>(keys, n, world, owner_counts);
     owner_scan_kernel<<<1, 1, 0, s>>>(owner_counts, world, cursors);
-    owner_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(keys, n, world, cursors, keys_by_owner, src_pos);
+    owner_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(keys, n, world, cursors, keys_by_owner, src_pos, 0, nullptr);
+    return cudaGetLastError();
+}
+
+__global__ void owner_fixed_init_kernel(uint32_t world, uint64_t capacity, unsigned long long* cursors) {
+    for (uint32_t w = threadIdx.x; w < world; w += blockDim.x) cursors[w] = (unsigned long long)w * capacity;
+}
+
+// Fixed-capacity routing: no bucket size ever has to reach the host (the all-to-all uses equal splits).
+cudaError_t launch_partition_fixed(const ctmr_key* keys, uint64_t n, uint32_t world, uint64_t capacity, ctmr_key* keys_by_owner,
+                                   uint32_t* src_pos, int* overflow, unsigned long long* cursors, cudaStream_t s) {
+    cudaError_t err = cudaMemsetAsync(keys_by_owner, 0, (size_t)world * capacity * sizeof(ctmr_key), s);  // valid = 0 everywhere
+    if (err == cudaSuccess) err = cudaMemsetAsync(src_pos, 0xFF, (size_t)world * capacity * sizeof(uint32_t), s);
+    if (err != cudaSuccess || !n) return err;
+    owner_fixed_init_kernel<<<1, 64, 0, s>>>(world, capacity, cursors);
+    owner_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(keys, n, world, cursors, keys_by_owner, src_pos, capacity, overflow);
     return cudaGetLastError();
 }
 
@@ -385,6 +407,7 @@ __global__ void __launch_bounds__(256) scatter_bits_kernel(const uint8_t* __rest
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     const uint32_t d = src_pos[j];
+    if (d == 0xFFFFFFFFu) return;  // an unused slot of the fixed-capacity layout
     if (a_dst) a_dst[d] = a[j];
     if (b_dst) b_dst[d] = b[j];
 }

@@ -241,6 +241,10 @@ class GpuCertDatabase:
         self._check(self._lib.ctmr_partition_keys_device(self._h, capi.ptr(keys), n, world, capi.ptr(keys_by_owner),
                                                          capi.ptr(src_pos), capi.ptr(owner_counts), stream))
 
+    def partition_keys_fixed_device(self, keys, n: int, world: int, capacity: int, keys_by_owner, src_pos, overflow, stream=None):
+        self._check(self._lib.ctmr_partition_keys_fixed_device(self._h, capi.ptr(keys), n, world, capacity, capi.ptr(keys_by_owner),
+                                                               capi.ptr(src_pos), capi.ptr(overflow), stream))
+
     def scatter_bits_device(self, was_unknown, first, src_pos, m: int, was_unknown_dst, first_dst, stream=None):
         self._check(self._lib.ctmr_scatter_bits_device(self._h, capi.ptr(was_unknown), capi.ptr(first), capi.ptr(src_pos), m,
                                                        capi.ptr(was_unknown_dst), capi.ptr(first_dst), stream))

@@ -42,6 +42,9 @@ class GpuOps:
     def partition(self, keys, n, world, keys_by_owner, src_pos, owner_counts):
         self.db.partition_keys_device(keys, n, world, keys_by_owner, src_pos, owner_counts, self._stream())
 
+    def partition_fixed(self, keys, n, world, capacity, keys_by_owner, src_pos, overflow):
+        self.db.partition_keys_fixed_device(keys, n, world, capacity, keys_by_owner, src_pos, overflow, self._stream())
+
     def reduce(self, keys, m, was_unknown, first):
         self.db.reduce_device(keys, m, was_unknown, first, self._stream())
 
@@ -55,8 +58,13 @@ class GpuOps:
 class ShardedReducer:
     """Reduce half across ranks for one chunk of key records produced by this rank's map half."""
 
-    def __init__(self, ops, device, n_issuer_slots: int, group=None, max_keys: int = 0):
+    def __init__(self, ops, device, n_issuer_slots: int, group=None, max_keys: int = 0, fixed_capacity: bool = False,
+                 slack: float = 1.25, min_slots: int = 1024):
+        """fixed_capacity=True selects the sync-free exchange: every rank sends the same number of key slots
+        (`slack` x its fair share, padded with invalid records) to every peer, so that no split size has to
+        travel through the host; `check_overflow()` tells afterwards whether some owner got more than that."""
         self.ops, self.device, self.group = ops, torch.device(device), group
+        self.fixed_capacity, self.slack, self.min_slots = fixed_capacity, slack, min_slots
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_issuer_slots = n_issuer_slots
@@ -84,6 +92,8 @@ class ShardedReducer:
         if self.world == 1:
             self.ops.reduce(keys, n, was_unknown, first)
             return
+        if self.fixed_capacity:
+            return self._reduce_chunk_fixed(keys, n, was_unknown, first)
         self._ensure(n, self._recv_cap)
         # 1. counting-sort the valid key records by owner rank
         self.ops.partition(keys, n, self.world, self.keys_by_owner, self.src_pos, self.owner_counts)
@@ -105,6 +115,41 @@ class ShardedReducer:
         was_unknown.zero_()
         first.zero_()
         self.ops.scatter(bu, bf, self.src_pos, m_send, was_unknown, first)
+
+    def _reduce_chunk_fixed(self, keys, n, was_unknown, first):
+        """The same routing without a host round trip: equal-split all-to-alls over fixed-capacity buckets."""
+        W = self.world
+        cap = max(64, -(-int(n * self.slack / W + self.min_slots) // 64) * 64)   # slots per (source, owner) pair
+        tot = W * cap
+        if getattr(self, "_fixed_cap", 0) < tot:
+            self.f_send = torch.empty((tot, KEY_BYTES), dtype=torch.uint8, device=self.device)
+            self.f_recv = torch.empty((tot, KEY_BYTES), dtype=torch.uint8, device=self.device)
+            self.f_src = torch.empty(tot, dtype=torch.int32, device=self.device)
+            self.f_bits = torch.empty((4, tot), dtype=torch.uint8, device=self.device)  # unknown/first at the owner, then back home
+            self._fixed_cap = tot
+        if not hasattr(self, "overflow"):
+            self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        send, recv, src = self.f_send[:tot], self.f_recv[:tot], self.f_src[:tot]
+        self.ops.partition_fixed(keys, n, W, cap, send, src, self.overflow)
+        dist.all_to_all_single(recv, send, group=self.group)                 # bucket w of every rank -> rank w
+        ou, of_, hu, hf = (self.f_bits[k, :tot] for k in range(4))
+        self.ops.reduce(recv, tot, ou, of_)                                  # invalid (padding) records are skipped
+        dist.all_to_all_single(hu, ou, group=self.group)                     # bits back, same geometry
+        dist.all_to_all_single(hf, of_, group=self.group)
+        was_unknown.zero_()
+        first.zero_()
+        self.ops.scatter(hu, hf, src, tot, was_unknown, first)               # padding slots carry src = 0xFFFFFFFF
+
+    def check_overflow(self):
+        """True if any fixed-capacity bucket overflowed on any rank since the last check (one host sync; call it once
+        per step or per run, not per chunk).  The affected chunks must be re-routed with the variable-size path."""
+        if not self.fixed_capacity or not hasattr(self, "overflow"):
+            return False
+        flag = self.overflow.clone()
+        if self.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        self.overflow.zero_()
+        return bool(int(flag.item()))
 
     def merged_histogram(self):
         """One all-reduce(sum) of [per-issuer unique counts || status counters] (north_star: the

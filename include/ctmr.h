@@ -242,6 +242,14 @@ int ctmr_profile_last(ctmr_ctx* ctx, float* map_ms, float* total_ms);
 int ctmr_partition_keys_device(ctmr_ctx* ctx, const ctmr_key* keys, uint64_t n, uint32_t world,
                                ctmr_key* keys_by_owner /* [n] */, uint32_t* src_pos /* [n] */,
                                uint64_t* owner_counts /* device [world] */, void* stream);
+/* The same routing with a FIXED capacity per owner, so that no bucket size has to reach the host and the key
+ * exchange can be an equal-split all-to-all: owner w's records go to keys_by_owner[w*capacity ..), unused slots
+ * keep valid = 0 (the reduce kernels skip them) and src_pos = 0xFFFFFFFF (ctmr_scatter_bits_device skips them).
+ * *overflow (device int32, cleared by the caller) becomes 1 if some owner had more than `capacity` records:
+ * the chunk must then be routed with ctmr_partition_keys_device instead. */
+int ctmr_partition_keys_fixed_device(ctmr_ctx* ctx, const ctmr_key* keys, uint64_t n, uint32_t world, uint64_t capacity,
+                                     ctmr_key* keys_by_owner /* [world*capacity] */, uint32_t* src_pos /* [world*capacity] */,
+                                     int32_t* overflow /* device */, void* stream);
 /* scatter routed-back result bits to entry order: dst[src_pos[j]] = bits[j], j < m */
 int ctmr_scatter_bits_device(ctmr_ctx* ctx, const uint8_t* was_unknown, const uint8_t* first_issuer_hour,
                              const uint32_t* src_pos, uint64_t m, uint8_t* was_unknown_dst,

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, chunks, q):
+def _worker(rank, world, port, n, chunks, q, fixed=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     import torch
@@ -36,7 +36,7 @@ def _worker(rank, world, port, n, chunks, q):
     dense = db.register_issuers(iblob, ioffs)
     assert (dense == np.arange(cfg.n_issuers)).all()
     ops = sharded.GpuOps(db)
-    red = sharded.ShardedReducer(ops, dev, n_issuer_slots=cfg.n_issuers)
+    red = sharded.ShardedReducer(ops, dev, n_issuer_slots=cfg.n_issuers, fixed_capacity=fixed)
     per = n // chunks
     cnt = per // world
     res = {}
@@ -59,6 +59,7 @@ def _worker(rank, world, port, n, chunks, q):
         torch.cuda.synchronize(dev)
         res[ch] = (lo, status.cpu().numpy(), sha.cpu().numpy(), wu.cpu().numpy(), fi.cpu().numpy())
     counts, stat = red.merged_histogram()
+    assert not red.check_overflow()
     db.check_device()
     q.put((rank, res, counts.cpu().numpy(), stat.cpu().numpy()))
     dist.barrier()
@@ -66,7 +67,8 @@ def _worker(rank, world, port, n, chunks, q):
 
 
 @pytest.mark.timeout(600)
-def test_sharded_gpu_path_matches_sequential_oracle(ora):
+@pytest.mark.parametrize("fixed", [False, True], ids=["ragged_all_to_all", "fixed_capacity_all_to_all"])
+def test_sharded_gpu_path_matches_sequential_oracle(ora, fixed):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -81,7 +83,7 @@ def test_sharded_gpu_path_matches_sequential_oracle(ora):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, chunks, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, chunks, q, fixed)) for r in range(world)]
     for p in procs:
         p.start()
     outs = [q.get(timeout=500) for _ in range(world)]

@@ -62,6 +62,22 @@ class EmulatedOps:
             pos += idx.size
         owner_counts.copy_(torch.from_numpy(cnt))
 
+    def partition_fixed(self, keys, n, world, capacity, keys_by_owner, src_pos, overflow):
+        """ctmr_partition_keys_fixed_device: bucket w = slots [w*capacity, (w+1)*capacity), padding invalid / src -1."""
+        recs = self._recs(keys, n)
+        owners = np.array([key_owner(int(r["exp_hour"]), int(r["issuer"]), world) if r["valid"] else -1 for r in recs])
+        out = keys_by_owner.numpy().reshape(-1).view(self.kd)
+        out[:world * capacity] = np.zeros(1, self.kd)
+        sp = src_pos.numpy()
+        sp[:world * capacity] = -1
+        for w in range(world):
+            idx = np.nonzero(owners == w)[0]
+            if idx.size > capacity:
+                overflow.fill_(1)
+                idx = idx[:capacity]
+            out[w * capacity:w * capacity + idx.size] = recs[idx]
+            sp[w * capacity:w * capacity + idx.size] = idx
+
     def reduce(self, keys, m, was_unknown, first):
         recs = self._recs(keys, m)
         bodies = [r.tobytes()[8:56] for r in recs]
@@ -81,8 +97,9 @@ class EmulatedOps:
 
     def scatter(self, was_unknown, first, src_pos, m, was_unknown_dst, first_dst):
         sp = src_pos.numpy()[:m].astype(np.int64)
-        was_unknown_dst.numpy()[sp] = was_unknown.numpy()[:m]
-        first_dst.numpy()[sp] = first.numpy()[:m]
+        live = sp >= 0  # 0xFFFFFFFF (= -1 as int32) marks an unused slot of the fixed-capacity layout
+        was_unknown_dst.numpy()[sp[live]] = was_unknown.numpy()[:m][live]
+        first_dst.numpy()[sp[live]] = first.numpy()[:m][live]
 
     def read_histogram(self, counts_dst, n_slots, status_dst):
         counts_dst.copy_(torch.from_numpy(self.counts[:n_slots]))
@@ -97,7 +114,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, chunks, q):
+def _worker(rank, world, port, n, chunks, q, fixed=False, slack=1.25, min_slots=1024):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -107,7 +124,7 @@ def _worker(rank, world, port, n, chunks, q):
     cfg = oracle.synth_cfg(n, len_mode=1, len_lo=512, len_hi=2048, dup_mode=1)
     iblob, ioffs = oracle.synth_issuers(cfg)
     ops = EmulatedOps(cfg.n_issuers)
-    red = sharded.ShardedReducer(ops, "cpu", n_issuer_slots=cfg.n_issuers)
+    red = sharded.ShardedReducer(ops, "cpu", n_issuer_slots=cfg.n_issuers, fixed_capacity=fixed, slack=slack, min_slots=min_slots)
     per = n // chunks
     res = {}
     for ch in range(chunks):
@@ -134,13 +151,14 @@ def _worker(rank, world, port, n, chunks, q):
         red.reduce_chunk(keys, cnt, wu, fi)
         res[ch] = (lo, wu.numpy().copy(), fi.numpy().copy())
     counts, status = red.merged_histogram()
-    q.put((rank, res, counts.numpy().copy(), status.numpy().copy()))
+    q.put((rank, res, counts.numpy().copy(), status.numpy().copy(), red.check_overflow()))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_reduce_matches_sequential_oracle(ora):
+@pytest.mark.parametrize("fixed", [False, True], ids=["ragged_all_to_all", "fixed_capacity_all_to_all"])
+def test_two_rank_reduce_matches_sequential_oracle(ora, fixed):
     n, chunks, world = 2400, 3, 2
     cfg = ora.synth_cfg(n, len_mode=1, len_lo=512, len_hi=2048, dup_mode=1)
     blob, offs, idx = ora.synth_corpus(cfg, 0, n)
@@ -151,16 +169,17 @@ def test_two_rank_reduce_matches_sequential_oracle(ora):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, chunks, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, chunks, q, fixed)) for r in range(world)]
     for p in procs:
         p.start()
     outs = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    assert not any(o[4] for o in outs)  # no bucket overflowed (never set on the ragged path)
     got_wu = np.zeros(n, np.uint8)
     got_fi = np.zeros(n, np.uint8)
-    for rank, res, counts, status in outs:
+    for rank, res, counts, status, _ in outs:
         for ch, (lo, wu, fi) in res.items():
             got_wu[lo:lo + wu.size] = wu
             got_fi[lo:lo + fi.size] = fi
@@ -175,9 +194,26 @@ def test_two_rank_reduce_matches_sequential_oracle(ora):
         rc, c = ora.parse_cert(der)
         dense_digest[k] = ora.issuer_id(der[c.spki_off:c.spki_off + c.spki_len])[0]
     oc = odb.issuer_counts()
-    for rank, res, counts, status in outs:
+    for rank, res, counts, status, _ in outs:
         assert {dense_digest[k]: int(v) for k, v in enumerate(counts) if v} == oc
         assert np.array_equal(status, odb.filter_counters().astype(np.int64))
+
+
+@pytest.mark.timeout(300)
+def test_fixed_capacity_overflow_is_reported_on_every_rank():
+    """Buckets sized below the fair share must overflow; the flag is all-reduced so that every rank re-routes."""
+    n, chunks, world = 1200, 1, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, chunks, q, True, 0.05, 0)) for r in range(world)]  # 64 slots per bucket
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(o[4] for o in outs)
 
 
 def test_key_owner_is_a_function_of_the_redis_set():
