@@ -238,7 +238,10 @@ def main():
     first = torch.empty(n, dtype=torch.uint8, device=dev)
     keys = torch.empty((n, capi.KEY_BYTES), dtype=torch.uint8, device=dev)
     ops = sharded.GpuOps(db)
-    red = sharded.ShardedReducer(ops, dev, n_issuer_slots=cfg.n_issuers, max_keys=n if world > 1 else 0)
+    # CTMR_FIXED_EXCHANGE=1: the sync-free fixed-capacity key exchange (opt-in until it has been measured on >= 2 GPUs)
+    fixed_exchange = world > 1 and os.environ.get("CTMR_FIXED_EXCHANGE", "0") == "1"
+    red = sharded.ShardedReducer(ops, dev, n_issuer_slots=cfg.n_issuers, max_keys=n if world > 1 else 0,
+                                 fixed_capacity=fixed_exchange)
     # Two streams: the INT-bound map half of sub-batch k+1 (stream A) overlaps the latency-bound reduce
     # half -- and, at N>1, the key exchange -- of sub-batch k (stream B).  Every launch, event and
     # collective of the timed region lives on one of them.
@@ -327,6 +330,8 @@ def main():
         dist.all_reduce(map_ms, op=dist.ReduceOp.MAX)
     elapsed_ms, map_ms = float(elapsed_ms.item()), float(map_ms.item())
     db.check_device(stream.cuda_stream)
+    if red.check_overflow():
+        raise RuntimeError("fixed-capacity key exchange overflowed: rerun without CTMR_FIXED_EXCHANGE")
 
     # ---- sanity inside the bench: the timed result is the real thing (cheap, size-independent checks)
     n_ok = int((status == 0).sum().item())
