@@ -906,9 +906,25 @@ int ctmr_check_device(ctmr_ctx* c, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------------------ the host-buffer batch
+static int process_batch_impl(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint64_t n, const uint8_t* issuer_blob,
+                              const uint64_t* issuer_offsets, uint32_t n_issuers, const uint32_t* issuer_idx, int64_t now_unix_ns,
+                              ctmr_out* out);
+
 int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint64_t n, const uint8_t* issuer_blob,
                        const uint64_t* issuer_offsets, uint32_t n_issuers, const uint32_t* issuer_idx, int64_t now_unix_ns,
                        ctmr_out* out) {
+    const int rc = process_batch_impl(c, blob, offsets, n, issuer_blob, issuer_offsets, n_issuers, issuer_idx, now_unix_ns, out);
+    if (rc != CTMR_OK && c && c->stages_ready) {  // no copy from / into the caller's buffers may outlive a failed call
+        const std::string keep = c->err;
+        for (Stage& s : c->stages) cudaStreamSynchronize(s.stream);
+        c->err = keep;
+    }
+    return rc;
+}
+
+static int process_batch_impl(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint64_t n, const uint8_t* issuer_blob,
+                              const uint64_t* issuer_offsets, uint32_t n_issuers, const uint32_t* issuer_idx, int64_t now_unix_ns,
+                              ctmr_out* out) {
     if (!c || !out || (n && (!blob || !offsets))) return fail(c, CTMR_E_INVALID, "bad argument");
     if (n == 0) return CTMR_OK;
     CU(c, cudaSetDevice(c->device));
@@ -1256,7 +1272,22 @@ int ctmr_evict_expired(ctmr_ctx* c, int64_t now_unix_sec, uint64_t* evicted_out)
 
 // ------------------------------------------------------------------------------------------------ CT wire-format front end
 // get-entries strings -> decode -> framing -> Chain[0] identification -> the path.
+static int process_raw_impl(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out);
+
 int ctmr_process_raw(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {
+    const int rc = process_raw_impl(c, b, out);
+    if (rc != CTMR_OK && c && c->fe) {
+        // an upload of the NEXT chunk may still be reading the caller's text and an output copy may still be writing
+        // the caller's arrays: neither may outlive the call
+        const std::string keep = c->err;
+        cudaStreamSynchronize(c->fe->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        c->err = keep;
+    }
+    return rc;
+}
+
+static int process_raw_impl(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {
     if (!c || !b || !out) return fail(c, CTMR_E_INVALID, "bad argument");
     if (b->n && (!b->text || !b->leaf_input_off || !b->leaf_input_len || !b->extra_data_off || !b->extra_data_len))
         return fail(c, CTMR_E_INVALID, "null batch buffers");
