@@ -121,3 +121,16 @@ def test_set_semantics_match_python_sets(ora, members, hour):
     key = ora.serials_key(hour, "issuer")
     assert cache.set_cardinality(key) == len(seen)
     assert cache.set_list(key) == sorted(seen)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.binary(min_size=0, max_size=400))
+def test_pem_expectation_matches_an_independent_encoder(data):
+    """conftest.go_pem is what the GPU's PEM output is compared with (encoding/pem.EncodeToMemory, 64-character lines,
+    storage/filesystemdatabase.go:171-175,197-198); pin it against Python's ssl module for every length residue."""
+    import ssl
+    from conftest import go_pem
+    if data:
+        assert go_pem(data).decode() == ssl.DER_cert_to_PEM_cert(data)
+    else:  # Go writes no body line for an empty block; ssl emits an empty one
+        assert go_pem(data) == b"-----BEGIN CERTIFICATE-----\n-----END CERTIFICATE-----\n"
