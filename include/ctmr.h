@@ -286,6 +286,13 @@ int ctmr_synth_truth_device(const struct ctmr_synth_cfg* cfg, uint64_t first, ui
  * offsets[0..n_issuers]; writes bytes when blob != NULL and cap suffices */
 uint64_t ctmr_synth_issuers_host(const struct ctmr_synth_cfg* cfg, uint64_t* offsets, uint8_t* blob, uint64_t cap);
 
+/* host-side: RFC 6962 get-entries response bodies (JSON, base64 leaf_input / extra_data; every third entry a
+ * precert_entry, chains of one or two certificates) for entries [first, first+n) in pages of `page` entries -- input
+ * for ctmr_process_raw (ctmr_frontend.h).  Returns the bytes needed; writes the text and the string spans when
+ * text != NULL and cap suffices. */
+uint64_t ctmr_synth_raw_pages_host(const struct ctmr_synth_cfg* cfg, uint64_t first, uint64_t n, uint32_t page, uint8_t* text,
+                                   uint64_t cap, uint64_t* leaf_off, uint32_t* leaf_len, uint64_t* extra_off, uint32_t* extra_len);
+
 #ifdef __cplusplus
 }
 #endif

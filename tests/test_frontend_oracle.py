@@ -251,3 +251,45 @@ def test_framing_agrees_with_an_independent_reading_of_rfc6962(ora, precert, ts,
     assert e.chain_count == len(want_chain)
     if want_chain:
         assert bytes(ed[e.chain0_off:e.chain0_off + e.chain0_len]) == want_chain[0]
+
+
+def test_host_page_generator_matches_the_python_encoders(ora):
+    """libctmr's ctmr_synth_raw_pages_host (what tools/bench_frontend.py feeds ctmr_process_raw with) against the same
+    pages built from the oracle's corpus with the Python encoders of ct_mapreduce_b200/frontend.py: byte for byte."""
+    import ctypes as C
+    import hashlib
+    from ct_mapreduce_b200 import build, capi
+    build.build()
+    n, page = 2300, 700
+    cfg = capi.synth_cfg(n, dup_mode=1, len_mode=1, len_lo=400, len_hi=3000)
+    L = capi.load()
+    need = L.ctmr_synth_raw_pages_host(C.byref(cfg), 0, n, page, None, 0, None, None, None, None)
+    text = np.zeros(need, np.uint8)
+    lo, ll, xo, xl = np.zeros(n, np.uint64), np.zeros(n, np.uint32), np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+    assert L.ctmr_synth_raw_pages_host(C.byref(cfg), 0, n, page, capi.ptr(text), need, capi.ptr(lo), capi.ptr(ll), capi.ptr(xo), capi.ptr(xl)) == need
+    ocfg = ora.synth_cfg(n, dup_mode=1, len_mode=1, len_lo=400, len_hi=3000)
+    blob, offs, idx = ora.synth_corpus(ocfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(ocfg)
+    issuers = [iblob[int(ioffs[k]):int(ioffs[k + 1])].tobytes() for k in range(ioffs.size - 1)]
+    entries = []
+    for i in range(n):
+        leaf, k = blob[int(offs[i]):int(offs[i + 1])].tobytes(), int(idx[i])
+        chain = [issuers[k], issuers[(k + 1) % len(issuers)]][:1 + i % 2]
+        if i % 3 == 0:
+            entries.append((fe.merkle_tree_leaf_precert(1_690_000_000_000 + i, hashlib.sha256(issuers[k]).digest(), fe.tbs_of(leaf)),
+                            fe.precert_chain_entry(leaf, chain)))
+        else:
+            entries.append((fe.merkle_tree_leaf_x509(1_690_000_000_000 + i, leaf), fe.certificate_chain(chain)))
+    bodies = [fe.get_entries_body(entries[a:a + page]) for a in range(0, n, page)]
+    assert text.tobytes() == b"".join(bodies)
+    spans, base = [], 0
+    for bd in bodies:
+        spans.append(fe.find_entry_spans(bd, base))
+        base += len(bd)
+    for got, j in ((lo, 0), (ll, 1), (xo, 2), (xl, 3)):
+        assert np.array_equal(got, np.concatenate([s[j] for s in spans]))
+    # and the oracle accepts every generated entry
+    for i in (0, 1, 2, 3, n - 1):
+        li = ora.b64_decode(text[int(lo[i]):int(lo[i]) + int(ll[i])].tobytes())
+        ed = ora.b64_decode(text[int(xo[i]):int(xo[i]) + int(xl[i])].tobytes())
+        assert ora.entry_from_leaf(li, ed)[0] == ora.FE_OK

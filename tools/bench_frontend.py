@@ -3,12 +3,12 @@
     python tools/bench_frontend.py [--entries 200000] [--steps 5] [--warmup 2]
 
 Synthesises get-entries pages (2/3 x509 entries, 1/3 precert entries, chains of one or two certificates) around
-the synthetic corpus, keeps the text in pinned host memory, and times whole ctmr_process_raw calls (host text in,
+the synthetic corpus with libctmr's threaded host generator, directly in pinned host memory, and times whole ctmr_process_raw calls (host text in,
 host results out).  Prints one JSON line: end-to-end entries/s, and the library's own CUDA-event split of a call
 into front-end kernels (base64, framing, Chain[0] identification) and the map/reduce path behind them.
 """
 import argparse
-import hashlib
+import ctypes as C
 import json
 import os
 import sys
@@ -23,30 +23,17 @@ NOW_NS = 1767225600 * 10**9
 
 
 def make_pages(n, page=1000):
+    """n synthetic entries as get-entries bodies, written by libctmr's host generator (ctmr_synth_raw_pages_host)
+    straight into pinned memory; tests/test_frontend_oracle.py checks that generator against the Python encoders."""
     cfg = capi.synth_cfg(n)
-    import torch
-    dev = torch.device("cuda:0")
-    blob, offs, idx, total = engine.synth_corpus_device(cfg, 0, n, dev)
-    blob, offs, idx = blob.cpu().numpy(), offs.cpu().numpy(), idx.cpu().numpy()
-    iblob, ioffs = engine.synth_issuers(cfg)
-    issuers = [iblob[int(ioffs[k]):int(ioffs[k + 1])].tobytes() for k in range(ioffs.size - 1)]
-    ikh = [hashlib.sha256(c).digest() for c in issuers]
-    entries = []
-    for i in range(n):
-        leaf = blob[int(offs[i]):int(offs[i + 1])].tobytes()
-        k = int(idx[i])
-        chain = [issuers[k], issuers[(k + 1) % len(issuers)]][: 1 + i % 2]
-        if i % 3 == 0:
-            entries.append((fe.merkle_tree_leaf_precert(1_690_000_000_000 + i, ikh[k], fe.tbs_of(leaf)), fe.precert_chain_entry(leaf, chain)))
-        else:
-            entries.append((fe.merkle_tree_leaf_x509(1_690_000_000_000 + i, leaf), fe.certificate_chain(chain)))
-    bodies = [fe.get_entries_body(entries[a:a + page]) for a in range(0, n, page)]
-    spans, base = [], 0
-    for bd in bodies:
-        spans.append(fe.find_entry_spans(bd, base))
-        base += len(bd)
-    lo, ll, xo, xl = (np.concatenate([s[j] for s in spans]) for j in range(4))
-    return b"".join(bodies), lo, ll, xo, xl, int(total)
+    L = capi.load()
+    need = L.ctmr_synth_raw_pages_host(C.byref(cfg), 0, n, page, None, 0, None, None, None, None)
+    pin = capi.PinnedBuffer(need)
+    lo, ll = np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+    xo, xl = np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+    got = L.ctmr_synth_raw_pages_host(C.byref(cfg), 0, n, page, pin.addr, need, capi.ptr(lo), capi.ptr(ll), capi.ptr(xo), capi.ptr(xl))
+    assert got == need
+    return pin, lo, ll, xo, xl
 
 
 def main():
@@ -56,11 +43,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     a = ap.parse_args()
     t0 = time.time()
-    text, lo, ll, xo, xl, leaf_bytes = make_pages(a.entries)
+    pin, lo, ll, xo, xl = make_pages(a.entries)
     gen_s = time.time() - t0
-    pin = capi.PinnedBuffer(len(text))
-    pin.view()[:] = np.frombuffer(text, np.uint8)
     tv = pin.view()
+    text = tv
     chars = int(ll.sum()) + int(xl.sum())
     with engine.GpuCertDatabase(log_expired_entries=True, table_capacity=1 << 22) as db:
         fe_ms = path_ms = 0.0
@@ -77,7 +63,7 @@ def main():
     assert ok == a.entries, (ok, a.entries)
     print(json.dumps({
         "metric": "ct_raw_entries_per_sec", "value": a.entries / dt, "unit": "entries/s", "entries": a.entries, "steps": a.steps,
-        "ms_per_call": dt * 1e3, "text_bytes": len(text), "base64_chars": chars, "leaf_der_bytes": leaf_bytes,
+        "ms_per_call": dt * 1e3, "text_bytes": len(text), "base64_chars": chars,
         "h2d_gbs": len(text) / dt / 1e9,
         "frontend_kernels_ms": fe_ms / a.steps, "frontend_kernels_chars_gbs": chars / (fe_ms / a.steps) / 1e6,
         "frontend_kernels_entries_per_sec": a.entries / (fe_ms / a.steps) * 1e3,
