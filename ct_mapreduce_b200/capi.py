@@ -33,7 +33,16 @@ EXPORTS = [
     "ctmr_check_device", "ctmr_reset_device", "ctmr_profile_last", "ctmr_preload_known", "ctmr_snapshot_size",
     "ctmr_snapshot_save", "ctmr_snapshot_load", "ctmr_evict_expired", "ctmr_sha256_ceiling_device", "ctmr_synth_offsets_device", "ctmr_synth_write_device", "ctmr_synth_truth_device", "ctmr_synth_issuers_host", "ctmr_synth_raw_pages_host",
     "ctmr_process_raw", "ctmr_frontend_profile_last",  # include/ctmr_frontend.h
+    # several GPUs: one process (group) / one process per GPU (peer)
+    "ctmr_group_create", "ctmr_group_destroy", "ctmr_group_last_error", "ctmr_group_size", "ctmr_group_member",
+    "ctmr_group_process_batch", "ctmr_group_issuer_counts", "ctmr_group_set_cardinality", "ctmr_group_status_counters",
+    "ctmr_group_table_stats", "ctmr_group_preload_known", "ctmr_group_evict_expired", "ctmr_group_reset",
+    "ctmr_peer_export", "ctmr_peer_attach", "ctmr_peer_barrier_device", "ctmr_peer_allreduce_histogram_device",
+    "ctmr_bind_host_to_device",
 ]
+PEER_HANDLE_BYTES = 128
+PEER_ROUNDS = 4
+E_PAIR_TABLE_FULL, E_META_TABLE_FULL, E_PEER_TIMEOUT, E_PEER = -8, -9, -10, -11
 
 
 class Config(C.Structure):
@@ -41,7 +50,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("table_capacity", C.c_uint64),
         ("max_batch_entries", C.c_uint64), ("max_batch_bytes", C.c_uint64), ("max_issuers", C.c_uint32),
         ("pair_capacity_log2", C.c_uint32), ("issuer_cn_filter", C.c_char_p), ("issuer_cn_filter_len", C.c_uint32),
-        ("log_expired_entries", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("log_expired_entries", C.c_uint32), ("flags", C.c_uint32), ("meta_capacity_log2", C.c_uint32),
     ]
 
 
@@ -155,6 +164,28 @@ def load():
     L.ctmr_synth_raw_pages_host.restype = u64
     L.ctmr_process_raw.argtypes = [vp, C.POINTER(RawBatch), C.POINTER(RawOut)]
     L.ctmr_frontend_profile_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
+    L.ctmr_group_create.argtypes = [C.POINTER(Config), vp, u32, C.POINTER(vp)]
+    L.ctmr_group_destroy.argtypes = [vp]
+    L.ctmr_group_destroy.restype = None
+    L.ctmr_group_last_error.argtypes = [vp]
+    L.ctmr_group_last_error.restype = C.c_char_p
+    L.ctmr_group_size.argtypes = [vp]
+    L.ctmr_group_size.restype = u32
+    L.ctmr_group_member.argtypes = [vp, u32]
+    L.ctmr_group_member.restype = vp
+    L.ctmr_group_process_batch.argtypes = [vp, vp, vp, u64, vp, vp, u32, vp, i64, C.POINTER(Out)]
+    L.ctmr_group_issuer_counts.argtypes = [vp, vp, vp, C.POINTER(C.c_size_t)]
+    L.ctmr_group_set_cardinality.argtypes = [vp, i64, vp, C.POINTER(u64)]
+    L.ctmr_group_status_counters.argtypes = [vp, vp]
+    L.ctmr_group_table_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.ctmr_group_preload_known.argtypes = [vp, i64, vp, vp, vp, u64]
+    L.ctmr_group_evict_expired.argtypes = [vp, i64, C.POINTER(u64)]
+    L.ctmr_group_reset.argtypes = [vp]
+    L.ctmr_peer_export.argtypes = [vp, vp]
+    L.ctmr_peer_attach.argtypes = [vp, u32, u32, vp]
+    L.ctmr_peer_barrier_device.argtypes = [vp, vp]
+    L.ctmr_peer_allreduce_histogram_device.argtypes = [vp, vp, u32, vp, vp]
+    L.ctmr_bind_host_to_device.argtypes = [C.c_int32]
     for name in EXPORTS:
         getattr(L, name)  # every symbol include/ctmr.h declares must resolve
     _lib = L

@@ -2,155 +2,11 @@
 // pipeline (H2D / kernels / D2H overlapped over three streams) and the device-resident entry points.
 // There is deliberately no CPU implementation of the path in this file or anywhere in the library:
 // without a CUDA device ctmr_create fails.
-#include <algorithm>
-#include <array>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <string>
-#include <unordered_map>
-#include <vector>
+#include "ctmr_ctx.cuh"
 
-#include "ctmr_kernels.cuh"
+thread_local std::string ctmr_host::g_create_error;
 
-using namespace ctmr;
-
-namespace {
-
-constexpr int kStages = 3;                      // host-API pipeline depth
-constexpr uint64_t kStageEntries = 1ull << 18;  // entries per pipeline stage
-constexpr uint64_t kStageBytes = 768ull << 20;  // leaf bytes per pipeline stage
-
-thread_local std::string g_create_error;
-
-// device side of the PEM output (ctmr_out.pem): one per host-pipeline stage and one for the front end
-struct PemStage {
-    uint64_t cap_entries = 0, cap_bytes = 0;
-    uint64_t *sizes = nullptr, *off = nullptr;
-    uint8_t* text = nullptr;
-    void* scan_temp = nullptr;
-    size_t scan_temp_bytes = 0;
-    std::vector<uint64_t> host_off;
-};
-
-struct Stage {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t reduced = nullptr;  // recorded after this stage's resolve kernel
-    uint8_t* blob = nullptr;
-    uint64_t* offsets = nullptr;
-    uint32_t* issuer_idx = nullptr;
-    uint8_t* status = nullptr;
-    uint8_t* sha = nullptr;
-    int64_t* exp_hour = nullptr;
-    uint32_t* serial_off = nullptr;
-    uint32_t* serial_len = nullptr;
-    uint8_t* was_unknown = nullptr;
-    uint8_t* first = nullptr;
-    ctmr_key* keys = nullptr;
-    uint32_t* slot_of = nullptr;
-    uint32_t* pair_slot = nullptr;
-    uint32_t* order = nullptr;
-    unsigned int* len_hist = nullptr;
-    uint32_t* spans = nullptr;       // [4][E]: issuer name off/len, crldp off/len
-    uint32_t* meta_slots = nullptr;  // [2*E]
-    uint8_t* first_meta = nullptr;   // [2][E]: first_issuer_dn, first_crldp
-    PemStage pem;                    // allocated when a caller first asks for PEM output
-};
-
-// one upload stage of the front end: a chunk's characters and string spans, device side and pinned host staging
-struct FeStage {
-    uint8_t* text = nullptr;  // [16 + cap_text + 64]
-    uint64_t *leaf_off = nullptr, *extra_off = nullptr, *h_leaf_off = nullptr, *h_extra_off = nullptr;
-    uint32_t *leaf_len = nullptr, *extra_len = nullptr, *h_leaf_len = nullptr, *h_extra_len = nullptr;
-    cudaEvent_t uploaded = nullptr, consumed = nullptr;
-    std::vector<uint8_t> pack;  // host staging of the slow path (strings scattered over more than one chunk of text)
-};
-
-// CT wire-format front end (include/ctmr_frontend.h): device buffers of one chunk + the device mirror of
-// the issuer registry keyed by certificate bytes
-struct FrontEnd {
-    uint64_t cap_entries = 0, cap_text = 0, cap_decoded = 0;
-    FeStage stage[2];          // upload double buffer
-    cudaStream_t copy_stream = nullptr;
-    uint64_t *pad_size = nullptr, *dec_off = nullptr;
-    uint32_t* dec_len = nullptr;
-    uint8_t *str_bad = nullptr, *decoded = nullptr;
-    void* scan_temp = nullptr;
-    size_t scan_temp_bytes = 0;
-    uint8_t *entry_status = nullptr, *entry_type = nullptr, *leaf_src = nullptr;
-    uint64_t *timestamp = nullptr, *leaf_abs = nullptr, *chain_abs = nullptr, *tbs_abs = nullptr;
-    uint32_t *leaf_rel = nullptr, *leaf_len_out = nullptr, *chain_len = nullptr, *tbs_len = nullptr, *issuer_idx = nullptr;
-    // outputs of the path for this chunk
-    uint8_t *status = nullptr, *sha = nullptr, *was_unknown = nullptr, *first = nullptr, *first_meta = nullptr;
-    int64_t* exp_hour = nullptr;
-    uint32_t *serial_off = nullptr, *serial_len = nullptr, *spans = nullptr;
-    // issuer certificates by bytes
-    IssuerCertSlot* slots_dev = nullptr;
-    std::vector<IssuerCertSlot> slots_host;
-    uint64_t slot_mask = 0, slots_used = 0;
-    uint8_t* arena = nullptr;
-    uint64_t arena_cap = 0, arena_used = 0;
-    uint64_t* pending = nullptr;
-    uint64_t pending_mask = 0;
-    uint32_t* unknown_list = nullptr;
-    uint32_t unknown_cap = 0;
-    unsigned int* unknown_count = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-    float fe_ms = 0.f, path_ms = 0.f;
-    uint64_t launches = 0;
-    PemStage pem;
-};
-
-}  // namespace
-
-struct ctmr_ctx {
-    int device = 0;
-    int sm_count = 148;
-    uint32_t flags = 0;
-    cudaStream_t stream = nullptr;
-    DeviceState st{};
-    FilterCfg filter{};
-    uint64_t next_index = 0;
-    uint64_t stage_entries = 0, stage_bytes = 0;
-    bool stages_ready = false;
-    Stage stages[kStages];
-    // issuer registry (Issuer.ID digests, storage/types.go:124-130)
-    std::unordered_map<std::string, uint32_t> issuer_by_der;
-    std::unordered_map<std::string, uint32_t> issuer_by_digest;
-    std::vector<std::array<uint8_t, 32>> digests;
-    uint32_t* issuer_map_dev = nullptr;
-    uint32_t issuer_map_cap = 0;
-    // scratch of the device-resident entry points
-    ctmr_key* keys_scratch = nullptr;
-    uint32_t* slot_scratch = nullptr;
-    uint32_t* pair_scratch = nullptr;
-    uint8_t* bits_scratch = nullptr;
-    uint32_t* meta_scratch = nullptr;  // [2*cap]
-    uint64_t scratch_cap = 0;
-    uint32_t* order_scratch = nullptr;  // length-bucketed order of the device entry points
-    uint64_t order_cap = 0;
-    unsigned int* len_hist = nullptr;
-    bool bucket_by_length = true;
-    bool fuse_insert = true;
-    // ctmr_process_device pipelines map (stream A) against reduce (stream B) over kSub sub-batches
-    cudaStream_t stream_a = nullptr, stream_b = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join_a = nullptr, ev_join_b = nullptr;
-    cudaEvent_t ev_map0[8] = {}, ev_map1[8] = {}, ev_red1[8] = {};
-    int last_sub = 0;
-    unsigned int* len_hist_sub[8] = {};
-    unsigned long long* small_dev = nullptr;  // [64] cursors / cardinality result
-    FrontEnd* fe = nullptr;
-    std::string err;
-};
-
-namespace {
-
-void fe_destroy(ctmr_ctx* c);
-void pem_free(PemStage& ps);
-int fe_add_issuer(ctmr_ctx* c, const std::string& der, uint32_t idx);
-int fe_clear_issuers(ctmr_ctx* c);
+namespace ctmr_host {
 
 int fail(ctmr_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -158,20 +14,19 @@ int fail(ctmr_ctx* ctx, int code, const std::string& msg) {
     return code;
 }
 
-#define CU(ctx, call)                                                                                   \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess) {                                                                        \
-            return fail((ctx), e_ == cudaErrorMemoryAllocation ? CTMR_E_NOMEM : CTMR_E_CUDA,             \
-                        std::string(#call) + ": " + cudaGetErrorString(e_));                            \
-        }                                                                                               \
-    } while (0)
-
 uint64_t pow2_at_least(uint64_t v) {
     uint64_t p = 1;
     while (p < v) p <<= 1;
     return p;
 }
+
+}  // namespace ctmr_host
+
+namespace {
+
+void fe_destroy(ctmr_ctx* c);
+int fe_add_issuer(ctmr_ctx* c, const std::string& der, uint32_t idx);
+int fe_clear_issuers(ctmr_ctx* c);
 
 // strings.Split(*ctconfig.IssuerCNFilter, ",") -- no trimming (ct-fetch.go:58)
 int build_filter(const ctmr_config* cfg, FilterCfg& f) {
@@ -197,34 +52,24 @@ int build_filter(const ctmr_config* cfg, FilterCfg& f) {
     return 0;
 }
 
-int ensure_stages(ctmr_ctx* c) {
-    if (c->stages_ready) return CTMR_OK;
-    for (int k = 0; k < kStages; ++k) {
-        Stage& s = c->stages[k];
-        const uint64_t E = c->stage_entries;
-        CU(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CU(c, cudaEventCreateWithFlags(&s.reduced, cudaEventDisableTiming));
-        CU(c, cudaMalloc(&s.blob, c->stage_bytes + 64));
-        CU(c, cudaMalloc(&s.offsets, (E + 1) * sizeof(uint64_t)));
-        CU(c, cudaMalloc(&s.issuer_idx, E * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&s.status, E));
-        CU(c, cudaMalloc(&s.sha, E * 32));
-        CU(c, cudaMalloc(&s.exp_hour, E * sizeof(int64_t)));
-        CU(c, cudaMalloc(&s.serial_off, E * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&s.serial_len, E * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&s.was_unknown, E));
-        CU(c, cudaMalloc(&s.first, E));
-        CU(c, cudaMalloc(&s.keys, E * sizeof(ctmr_key)));
-        CU(c, cudaMalloc(&s.slot_of, E * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&s.pair_slot, E * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&s.order, E * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&s.len_hist, 256 * sizeof(unsigned int)));
-        CU(c, cudaMalloc(&s.spans, 4 * E * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&s.meta_slots, 2 * E * sizeof(uint32_t)));
-        CU(c, cudaMalloc(&s.first_meta, 2 * E));
-    }
-    c->stages_ready = true;
-    return CTMR_OK;
+SharedLayout make_layout(uint64_t table_slots, uint64_t pair_slots, uint64_t meta_slots, uint32_t max_issuers) {
+    SharedLayout l;
+    auto take = [&](size_t bytes) {
+        const size_t at = l.total;
+        l.total += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    l.flags = take((kPeerChannels + 1) * kMaxWorld * sizeof(unsigned long long));
+    l.reg_counter = take(sizeof(unsigned long long));
+    l.status_counts = take(CTMR_ST__COUNT * sizeof(unsigned long long));
+    l.issuer_counts = take((size_t)max_issuers * sizeof(unsigned long long));
+    l.reg_digests = take((size_t)max_issuers * 32);
+    l.reg_mask = pow2_at_least(2ull * max_issuers) - 1;
+    l.reg_slots = take((size_t)(l.reg_mask + 1) * sizeof(IssuerRegSlot));
+    l.meta = take((size_t)meta_slots * sizeof(MetaSlot));
+    l.pairs = take((size_t)pair_slots * sizeof(PairSlot));
+    l.table = take((size_t)table_slots * sizeof(KnownSlot));
+    return l;
 }
 
 int ensure_scratch(ctmr_ctx* c, uint64_t n) {
@@ -243,8 +88,11 @@ int ensure_scratch(ctmr_ctx* c, uint64_t n) {
     return CTMR_OK;
 }
 
-void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, MapParams& p, int counter_slot = 3,
-                     uint32_t* fused_slot_of = nullptr) {
+}  // namespace
+
+namespace ctmr_host {
+void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, MapParams& p, int counter_slot,
+                     uint32_t* fused_slot_of) {
     std::memset(&p, 0, sizeof p);
     p.blob = b->blob;
     p.blob_bytes = b->blob_bytes;
@@ -284,14 +132,52 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
     p.status_counts = c->st.status_counts;
     p.work_counter = c->small_dev + 84 + counter_slot;  // one per pipeline stage + one for the device entry points
     p.filter = c->filter;
-    if (fused_slot_of && p.keys) {  // K_insert fused into K_map (single-GPU paths)
-        p.table = c->st.table;
+    if (fused_slot_of && p.keys) {  // K_insert fused into K_map: straight into the owner's table, local or over NVLink
+        for (uint32_t r = 0; r < kMaxWorld; ++r) p.table[r] = c->st.peer.table[r];
+        p.world = c->st.peer.world;
         p.table_mask = c->st.table_mask;
         p.error_flag = c->st.error_flag;
         p.slot_of = fused_slot_of;
     }
 }
 
+// views of every rank's shared region: the tables K_map / K_resolve address, the flags and histograms of the
+// cross-process barrier and all-reduce, the issuer registry in rank 0's region
+void attach_views(ctmr_ctx* c, uint8_t* const* bases, uint32_t world, uint32_t rank) {
+    const SharedLayout& l = c->lay;
+    c->st.peer = PeerTables{};
+    c->pf = PeerFlags{};
+    for (uint32_t r = 0; r < world; ++r) {
+        c->st.peer.table[r] = reinterpret_cast<KnownSlot*>(bases[r] + l.table);
+        c->st.peer.pairs[r] = reinterpret_cast<PairSlot*>(bases[r] + l.pairs);
+        c->st.peer.meta[r] = reinterpret_cast<MetaSlot*>(bases[r] + l.meta);
+        c->pf.flags[r] = reinterpret_cast<unsigned long long*>(bases[r] + l.flags);
+        c->pf.issuer_counts[r] = reinterpret_cast<unsigned long long*>(bases[r] + l.issuer_counts);
+        c->pf.status_counts[r] = reinterpret_cast<unsigned long long*>(bases[r] + l.status_counts);
+    }
+    c->st.peer.world = c->pf.world = world;
+    c->st.peer.rank = c->pf.rank = rank;
+    c->pf.timeout_ns = 60000ull * 1000000ull;
+    if (const char* ev = getenv("CTMR_PEER_TIMEOUT_MS")) {
+        const unsigned long long ms = strtoull(ev, nullptr, 10);
+        if (ms) c->pf.timeout_ns = ms * 1000000ull;
+    }
+    c->reg.slots = reinterpret_cast<IssuerRegSlot*>(bases[0] + l.reg_slots);
+    c->reg.mask = l.reg_mask;
+    c->reg.counter = reinterpret_cast<unsigned long long*>(bases[0] + l.reg_counter);
+    c->reg.by_index = bases[0] + l.reg_digests;
+    c->reg.max_issuers = c->st.max_issuers;
+}
+
+int peer_barrier(ctmr_ctx* c, uint32_t channel, cudaStream_t s) {
+    if (c->peer_mode != PEER_IPC) return CTMR_OK;
+    CU(c, launch_peer_barrier(c->pf, channel, ++c->epoch[channel], c->st.error_flag, s));
+    return CTMR_OK;
+}
+}  // namespace ctmr_host
+
+namespace {
+int ensure_scratch(ctmr_ctx* c, uint64_t n);
 int reduce_on(ctmr_ctx* c, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, uint32_t* pair_slot, uint8_t* was_unknown,
               uint8_t* first, cudaStream_t s, bool already_inserted = false) {
     if (!already_inserted) CU(c, launch_insert(c->st, keys, m, slot_of, s));
@@ -300,45 +186,6 @@ int reduce_on(ctmr_ctx* c, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, 
     return CTMR_OK;
 }
 
-
-// ------------------------------------------------------------------------------------------------ PEM output
-void pem_free(PemStage& ps) {
-    cudaFree(ps.sizes); cudaFree(ps.off); cudaFree(ps.text); cudaFree(ps.scan_temp);
-    ps = PemStage{};
-}
-
-int pem_ensure(ctmr_ctx* c, PemStage& ps, uint64_t entries, uint64_t der_bytes) {
-    const uint64_t need_bytes = der_bytes / 3 * 4 + der_bytes / 48 + 64 * entries + 256;  // body + newlines + boundary lines
-    if (ps.cap_entries >= entries && ps.cap_bytes >= need_bytes) return CTMR_OK;
-    CU(c, cudaDeviceSynchronize());
-    pem_free(ps);
-    CU(c, cudaMalloc(&ps.sizes, (entries + 1) * 8));
-    CU(c, cudaMalloc(&ps.off, (entries + 1) * 8));
-    CU(c, cudaMalloc(&ps.text, need_bytes));
-    ps.scan_temp_bytes = pem_scan_temp_bytes(entries + 1);
-    CU(c, cudaMalloc(&ps.scan_temp, ps.scan_temp_bytes ? ps.scan_temp_bytes : 16));
-    ps.cap_entries = entries;
-    ps.cap_bytes = need_bytes;
-    return CTMR_OK;
-}
-
-// Encodes the selected certificates of one chunk on `s`, waits for it, and appends the text to the caller's
-// buffer at *base (host).  pem_off_out[i] (i < cnt) = absolute start of entry i's text.
-int pem_chunk(ctmr_ctx* c, PemStage& ps, const uint8_t* blob, const uint64_t* offsets, const uint32_t* lens, const uint8_t* select,
-              uint64_t cnt, const ctmr_out* out, uint64_t first, uint64_t* base, cudaStream_t s) {
-    CU(c, launch_pem_encode(blob, offsets, lens, select, cnt, ps.sizes, ps.scan_temp, ps.scan_temp_bytes, ps.off, ps.text, ps.cap_bytes,
-                            c->st.error_flag, c->sm_count, s));
-    ps.host_off.resize(cnt + 1);
-    CU(c, cudaMemcpyAsync(ps.host_off.data(), ps.off, (cnt + 1) * 8, cudaMemcpyDeviceToHost, s));
-    CU(c, cudaStreamSynchronize(s));
-    const uint64_t total = ps.host_off[cnt];
-    if (total > ps.cap_bytes) return fail(c, CTMR_E_BATCH_TOO_LARGE, "PEM staging too small (internal sizing)");
-    if (*base + total > out->pem_cap) return fail(c, CTMR_E_BATCH_TOO_LARGE, "ctmr_out.pem_cap too small for the new certificates' PEM");
-    if (total) CU(c, cudaMemcpyAsync(out->pem + *base, ps.text, total, cudaMemcpyDeviceToHost, s));
-    for (uint64_t i = 0; i < cnt; ++i) out->pem_off[first + i] = *base + ps.host_off[i];
-    *base += total;
-    return CTMR_OK;
-}
 
 // ------------------------------------------------------------------------------------------------ front end plumbing
 void fe_destroy(ctmr_ctx* c) {
@@ -563,23 +410,33 @@ int ctmr_create(const ctmr_config* cfg, ctmr_ctx** out) {
         return bail(CTMR_E_INVALID);
     }
     c->st.table_mask = cap - 1;
-    CUC(cudaMalloc(&c->st.table, cap * sizeof(KnownSlot)));
-    CUC(cudaMemsetAsync(c->st.table, 0, cap * sizeof(KnownSlot), c->stream));
     const uint32_t plog = cfg->pair_capacity_log2 ? cfg->pair_capacity_log2 : 24;
+    const uint32_t mlog = cfg->meta_capacity_log2 ? cfg->meta_capacity_log2 : 20;
+    if (plog > 32 || mlog > 26) {
+        c->err = "pair_capacity_log2 above 32 or meta_capacity_log2 above 26";
+        return bail(CTMR_E_INVALID);
+    }
     c->st.pair_mask = (1ull << plog) - 1;
-    CUC(cudaMalloc(&c->st.pairs, (c->st.pair_mask + 1) * sizeof(PairSlot)));
-    CUC(cudaMemsetAsync(c->st.pairs, 0, (c->st.pair_mask + 1) * sizeof(PairSlot), c->stream));
-    c->st.meta_mask = (1ull << 20) - 1;  // IssuerMetadata string identities: O(issuers x few)
-    CUC(cudaMalloc(&c->st.meta, (c->st.meta_mask + 1) * sizeof(MetaSlot)));
-    CUC(cudaMemsetAsync(c->st.meta, 0, (c->st.meta_mask + 1) * sizeof(MetaSlot), c->stream));
+    c->st.meta_mask = (1ull << mlog) - 1;  // IssuerMetadata string identities: O(issuers x few)
     c->st.max_issuers = cfg->max_issuers ? cfg->max_issuers : 65536;
-    CUC(cudaMalloc(&c->st.issuer_counts, c->st.max_issuers * sizeof(unsigned long long)));
-    CUC(cudaMemsetAsync(c->st.issuer_counts, 0, c->st.max_issuers * sizeof(unsigned long long), c->stream));
+    // ONE allocation for everything another rank of a group may address (tables, histograms, barrier flags, issuer
+    // registry): one CUDA IPC handle exports it; on a single GPU it is simply this ctx's state
+    c->lay = make_layout(cap, c->st.pair_mask + 1, c->st.meta_mask + 1, c->st.max_issuers);
+    CUC(cudaMalloc(&c->shared, c->lay.total));
+    CUC(cudaMemsetAsync(c->shared, 0, c->lay.total, c->stream));
+    c->st.table = reinterpret_cast<KnownSlot*>(c->shared + c->lay.table);
+    c->st.pairs = reinterpret_cast<PairSlot*>(c->shared + c->lay.pairs);
+    c->st.meta = reinterpret_cast<MetaSlot*>(c->shared + c->lay.meta);
+    c->st.issuer_counts = reinterpret_cast<unsigned long long*>(c->shared + c->lay.issuer_counts);
+    c->st.status_counts = reinterpret_cast<unsigned long long*>(c->shared + c->lay.status_counts);
     CUC(cudaMalloc(&c->small_dev, 128 * sizeof(unsigned long long)));
     CUC(cudaMemsetAsync(c->small_dev, 0, 128 * sizeof(unsigned long long), c->stream));
-    c->st.status_counts = c->small_dev + 64;  // [8]
     c->st.slots_used = c->small_dev + 72;     // [1]
     c->st.error_flag = reinterpret_cast<int*>(c->small_dev + 73);
+    {
+        uint8_t* self[1] = {c->shared};
+        attach_views(c, self, 1, 0);  // a single GPU is a group of one
+    }
     c->stage_entries = cfg->max_batch_entries ? (cfg->max_batch_entries < kStageEntries ? cfg->max_batch_entries : kStageEntries)
                                               : kStageEntries;
     const uint64_t want_bytes = cfg->max_batch_bytes ? cfg->max_batch_bytes : c->stage_entries * 2048ull;
@@ -597,17 +454,12 @@ void ctmr_destroy(ctmr_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (Stage& s : c->stages) {
-        cudaFree(s.blob); cudaFree(s.offsets); cudaFree(s.issuer_idx); cudaFree(s.status); cudaFree(s.sha);
-        cudaFree(s.exp_hour); cudaFree(s.serial_off); cudaFree(s.serial_len); cudaFree(s.was_unknown); cudaFree(s.first);
-        cudaFree(s.keys); cudaFree(s.slot_of); cudaFree(s.pair_slot); cudaFree(s.order); cudaFree(s.len_hist); cudaFree(s.spans); cudaFree(s.meta_slots); cudaFree(s.first_meta);
-        pem_free(s.pem);
-        if (s.reduced) cudaEventDestroy(s.reduced);
-        if (s.stream) cudaStreamDestroy(s.stream);
-    }
-    cudaFree(c->st.table); cudaFree(c->st.pairs); cudaFree(c->st.issuer_counts); cudaFree(c->small_dev);
+    stages_destroy(c);
+    for (uint32_t r = 0; r < kMaxWorld; ++r)
+        if (c->ipc_base[r]) cudaIpcCloseMemHandle(c->ipc_base[r]);
+    cudaFree(c->shared); cudaFree(c->small_dev);
     cudaFree(c->issuer_map_dev); cudaFree(c->keys_scratch); cudaFree(c->slot_scratch); cudaFree(c->pair_scratch);
-    cudaFree(c->bits_scratch); cudaFree(c->meta_scratch); cudaFree(c->order_scratch); cudaFree(c->len_hist); cudaFree(c->st.meta);
+    cudaFree(c->bits_scratch); cudaFree(c->meta_scratch); cudaFree(c->order_scratch); cudaFree(c->len_hist);
     for (int k = 0; k < 8; ++k) {
         cudaFree(c->len_hist_sub[k]);
         if (c->ev_map0[k]) cudaEventDestroy(c->ev_map0[k]);
@@ -625,6 +477,86 @@ void ctmr_destroy(ctmr_ctx* c) {
 }
 
 // ------------------------------------------------------------------------------------------------ issuers
+// The registry (Issuer.ID digest -> dense index) is a find-or-insert table in the device memory of the group's rank 0,
+// reached with system-scope atomics: whichever rank meets an issuer first, every rank gets the same index for it.
+// The host keeps memos only (DER -> index, digest -> index, index -> digest), filled from the device.
+}  // extern "C"
+
+namespace ctmr_host {
+
+int refresh_digests(ctmr_ctx* c) {
+    unsigned long long cnt = 0;
+    CU(c, cudaMemcpyAsync(&cnt, c->reg.counter, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (cnt > c->reg.max_issuers) cnt = c->reg.max_issuers;
+    const size_t have = c->digests.size();
+    if (cnt <= have) return CTMR_OK;
+    std::vector<uint8_t> rows((cnt - have) * 32);
+    CU(c, cudaMemcpyAsync(rows.data(), c->reg.by_index + 32 * have, rows.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = have; i < cnt; ++i) {
+        const uint8_t* row = rows.data() + 32 * (i - have);
+        bool zero = true;
+        for (int k = 0; k < 32; ++k) zero &= row[k] == 0;
+        if (zero) break;  // index handed out by another rank's kernel, digest not written yet: next time
+        std::array<uint8_t, 32> a;
+        std::memcpy(a.data(), row, 32);
+        c->digests.push_back(a);
+        c->issuer_by_digest.emplace(std::string(reinterpret_cast<const char*>(row), 32), (uint32_t)i);
+    }
+    return CTMR_OK;
+}
+
+// digest -> dense index; `insert` registers an unknown digest (state written by an earlier process, preloads)
+int lookup_digest(ctmr_ctx* c, const uint8_t digest[32], bool insert, uint32_t* idx_out, bool* found) {
+    const std::string dk(reinterpret_cast<const char*>(digest), 32);
+    *found = false;
+    auto it = c->issuer_by_digest.find(dk);
+    if (it == c->issuer_by_digest.end()) {
+        int rc = refresh_digests(c);
+        if (rc) return rc;
+        it = c->issuer_by_digest.find(dk);
+    }
+    if (it != c->issuer_by_digest.end()) {
+        *idx_out = it->second;
+        *found = true;
+        return CTMR_OK;
+    }
+    if (!insert) return CTMR_OK;
+    uint8_t* d_dig = reinterpret_cast<uint8_t*>(c->small_dev + 100);  // [4] words = 32 bytes
+    uint32_t* d_idx = reinterpret_cast<uint32_t*>(c->small_dev + 104);
+    uint32_t idx = CTMR_ISSUER_BAD;
+    CU(c, cudaMemcpyAsync(d_dig, digest, 32, cudaMemcpyHostToDevice, c->stream));
+    CU(c, launch_issuer_registry(c->reg, d_dig, nullptr, 1, d_idx, c->st.error_flag, c->stream));
+    CU(c, cudaMemcpyAsync(&idx, d_idx, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (idx == CTMR_ISSUER_BAD) {
+        ctmr_check_device(c, nullptr);  // clears the flag
+        return fail(c, CTMR_E_TOO_MANY_ISSUERS, "more distinct issuers than config.max_issuers");
+    }
+    c->issuer_by_digest.emplace(dk, idx);
+    *idx_out = idx;
+    *found = true;
+    return refresh_digests(c);
+}
+
+int upload_issuer_map(ctmr_ctx* c, const uint32_t* dense, uint32_t n) {
+    if (n > c->issuer_map_cap) {
+        cudaFree(c->issuer_map_dev);
+        c->issuer_map_dev = nullptr;
+        c->issuer_map_cap = 0;
+        CU(c, cudaMalloc(&c->issuer_map_dev, (size_t)n * sizeof(uint32_t)));
+        c->issuer_map_cap = n;
+    }
+    CU(c, cudaMemcpyAsync(c->issuer_map_dev, dense, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CTMR_OK;
+}
+
+}  // namespace ctmr_host
+
+extern "C" {
+
 int ctmr_register_issuers(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint32_t* dense_out) {
     if (!c || (n && (!blob || !offsets || !dense_out))) return fail(c, CTMR_E_INVALID, "bad argument");
     CU(c, cudaSetDevice(c->device));
@@ -645,7 +577,8 @@ int ctmr_register_issuers(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offs
         }
     }
     if (!fresh.empty()) {
-        // only never-seen certificates go to the GPU: parse + SHA-256(SPKI) there, ids come back
+        // only never-seen certificates go to the GPU: parse + SHA-256(SPKI) there, then find-or-insert of the digest
+        // in the registry (rank 0's memory); indices and digests come back
         std::vector<uint8_t> packed;
         std::vector<uint64_t> poff(1, 0);
         for (uint32_t f : fresh) {
@@ -655,54 +588,61 @@ int ctmr_register_issuers(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offs
         const uint32_t nf = (uint32_t)fresh.size();
         uint8_t *d_blob = nullptr, *d_dig = nullptr, *d_ok = nullptr;
         uint64_t* d_off = nullptr;
+        uint32_t* d_idx = nullptr;
+        auto release = [&]() { cudaFree(d_blob); cudaFree(d_off); cudaFree(d_dig); cudaFree(d_ok); cudaFree(d_idx); };
         CU(c, cudaMalloc(&d_blob, packed.size() + 64));
         CU(c, cudaMalloc(&d_off, poff.size() * sizeof(uint64_t)));
         CU(c, cudaMalloc(&d_dig, nf * 32));
         CU(c, cudaMalloc(&d_ok, nf));
+        CU(c, cudaMalloc(&d_idx, nf * sizeof(uint32_t)));
         CU(c, cudaMemcpyAsync(d_blob, packed.data(), packed.size(), cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemcpyAsync(d_off, poff.data(), poff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
         CU(c, launch_issuer_prepare(d_blob, d_off, nf, d_dig, d_ok, c->stream));
+        CU(c, launch_issuer_registry(c->reg, d_dig, d_ok, nf, d_idx, c->st.error_flag, c->stream));
         std::vector<uint8_t> dig(nf * 32), ok(nf);
+        std::vector<uint32_t> idx(nf);
         CU(c, cudaMemcpyAsync(dig.data(), d_dig, nf * 32, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaMemcpyAsync(ok.data(), d_ok, nf, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(idx.data(), d_idx, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
-        cudaFree(d_blob); cudaFree(d_off); cudaFree(d_dig); cudaFree(d_ok);
+        release();
         for (uint32_t i = 0; i < nf; ++i) {
-            uint32_t idx = CTMR_ISSUER_BAD;
-            if (ok[i]) {
-                std::string dk(reinterpret_cast<const char*>(dig.data() + 32 * i), 32);
-                auto it = c->issuer_by_digest.find(dk);
-                if (it != c->issuer_by_digest.end()) {
-                    idx = it->second;
-                } else {
-                    if (c->digests.size() >= c->st.max_issuers)
-                        return fail(c, CTMR_E_TOO_MANY_ISSUERS, "more distinct issuers than config.max_issuers");
-                    idx = (uint32_t)c->digests.size();
-                    std::array<uint8_t, 32> a;
-                    std::memcpy(a.data(), dig.data() + 32 * i, 32);
-                    c->digests.push_back(a);
-                    c->issuer_by_digest.emplace(std::move(dk), idx);
-                }
+            if (ok[i] && idx[i] == CTMR_ISSUER_BAD) {
+                ctmr_check_device(c, nullptr);  // clears the flag
+                return fail(c, CTMR_E_TOO_MANY_ISSUERS, "more distinct issuers than config.max_issuers");
             }
-            c->issuer_by_der.emplace(ders[fresh[i]], idx);
+            if (ok[i]) c->issuer_by_digest.emplace(std::string(reinterpret_cast<const char*>(dig.data() + 32 * i), 32), idx[i]);
+            c->issuer_by_der.emplace(ders[fresh[i]], idx[i]);
             if (c->fe) {
-                int rc2 = fe_add_issuer(c, ders[fresh[i]], idx);
+                int rc2 = fe_add_issuer(c, ders[fresh[i]], idx[i]);
                 if (rc2) return rc2;
             }
         }
         for (uint32_t k = 0; k < n; ++k)
             if (dense_out[k] == CTMR_ISSUER_NONE) dense_out[k] = c->issuer_by_der[ders[k]];
+        int rc = refresh_digests(c);
+        if (rc) return rc;
     }
     return CTMR_OK;
 }
 
 int ctmr_issuer_digest(ctmr_ctx* c, uint32_t idx, uint8_t out[32]) {
-    if (!c || !out || idx >= c->digests.size()) return fail(c, CTMR_E_INVALID, "no such issuer");
+    if (!c || !out) return fail(c, CTMR_E_INVALID, "bad argument");
+    if (idx >= c->digests.size()) {
+        CU(c, cudaSetDevice(c->device));
+        int rc = refresh_digests(c);  // another rank of the group may have registered it
+        if (rc) return rc;
+    }
+    if (idx >= c->digests.size()) return fail(c, CTMR_E_INVALID, "no such issuer");
     std::memcpy(out, c->digests[idx].data(), 32);
     return CTMR_OK;
 }
 
-uint32_t ctmr_issuer_count(ctmr_ctx* c) { return c ? (uint32_t)c->digests.size() : 0; }
+uint32_t ctmr_issuer_count(ctmr_ctx* c) {
+    if (!c) return 0;
+    if (cudaSetDevice(c->device) == cudaSuccess) refresh_digests(c);
+    return (uint32_t)c->digests.size();
+}
 
 // ------------------------------------------------------------------------------------------------ device entry points
 int ctmr_map_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, void* stream) {
@@ -772,7 +712,15 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
     cudaStream_t user = stream ? (cudaStream_t)stream : c->stream;
     // The map half is INT-pipe bound and the reduce half is latency/atomic bound: run sub-batch
     // k+1's K_map (stream A) while sub-batch k's insert/resolve/pairs run (stream B).
-    const int nsub = b->n >= (1u << 21) ? 4 : (b->n >= (1u << 18) ? 2 : 1);
+    // In a multi-process group the call is collective: every rank runs CTMR_PEER_ROUNDS rounds (empty ones included)
+    // and meets the others at two barriers per round; round k of rank r carries the global indices
+    // first_index + (k * world + r) * E .. , i.e. the rounds are ordered, and inside a round the ranks.
+    const uint32_t world = c->st.peer.world, rank = c->st.peer.rank;
+    const bool coll = c->peer_mode == PEER_IPC && world > 1;
+    if (c->peer_mode == PEER_GROUP && world > 1)
+        return fail(c, CTMR_E_INVALID, "members of an in-process group are driven through ctmr_group_process_batch");
+    const int nsub = coll ? (int)CTMR_PEER_ROUNDS : (b->n >= (1u << 21) ? 4 : (b->n >= (1u << 18) ? 2 : 1));
+    const uint64_t per_round = (b->n + nsub - 1) / nsub;
     ctmr_key* keys = o->keys ? o->keys : c->keys_scratch;
     uint8_t* wu = o->was_unknown ? o->was_unknown : c->bits_scratch;
     uint8_t* fi = o->first_issuer_hour ? o->first_issuer_hour : c->bits_scratch + b->n;
@@ -780,13 +728,21 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
     CU(c, cudaStreamWaitEvent(c->stream_a, c->ev_fork, 0));
     CU(c, cudaStreamWaitEvent(c->stream_b, c->ev_fork, 0));
     for (int k = 0; k < nsub; ++k) {
-        const uint64_t lo = b->n * k / nsub, hi = b->n * (k + 1) / nsub, cnt = hi - lo;
+        uint64_t lo, hi;
+        if (coll) {
+            lo = std::min<uint64_t>(b->n, per_round * k);
+            hi = std::min<uint64_t>(b->n, per_round * (k + 1));
+        } else {
+            lo = b->n * k / nsub;
+            hi = b->n * (k + 1) / nsub;
+        }
+        const uint64_t cnt = hi - lo;
         ctmr_dev_batch sb = *b;
         sb.offsets = b->offsets + lo;
         sb.lens = b->lens ? b->lens + lo : nullptr;
         sb.n = cnt;
         sb.issuer_idx = b->issuer_idx ? b->issuer_idx + lo : nullptr;
-        sb.first_index = b->first_index + lo;
+        sb.first_index = coll ? b->first_index + ((uint64_t)k * world + rank) * per_round : b->first_index + lo;
         ctmr_dev_out so{};
         so.status = o->status ? o->status + lo : nullptr;
         so.sha256 = o->sha256 ? o->sha256 + lo * 32 : nullptr;
@@ -808,13 +764,20 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
         CU(c, launch_map(p, c->sm_count, c->stream_a));
         CU(c, cudaEventRecord(c->ev_map1[k], c->stream_a));
         CU(c, cudaStreamWaitEvent(c->stream_b, c->ev_map1[k], 0));
-        rc = reduce_on(c, keys + lo, cnt, c->slot_scratch + lo, c->pair_scratch + lo, wu + lo, fi + lo, c->stream_b,
-                       c->fuse_insert);
+        cudaStream_t sbm = c->stream_b;
+        if (!c->fuse_insert) CU(c, launch_insert(c->st, keys + lo, cnt, c->slot_scratch + lo, sbm));
+        rc = peer_barrier(c, CH_DEV_MAP, sbm);  // every rank's inserts of rounds <= k are in the owners' tables
         if (rc) return rc;
-        if (want_meta)  // IssuerMetadata string identities of this sub-batch's new certificates
-            CU(c, launch_meta(c->st, sb.blob, sb.offsets, keys + lo, cnt, wu + lo, so.issuer_name_off, so.issuer_name_len, so.crldp_off,
-                              so.crldp_len, c->meta_scratch + 2 * lo, o->first_issuer_dn ? o->first_issuer_dn + lo : nullptr,
-                              o->first_crldp ? o->first_crldp + lo : nullptr, c->stream_b));
+        CU(c, launch_resolve(c->st, keys + lo, cnt, c->slot_scratch + lo, c->pair_scratch + lo, wu + lo, sbm));
+        if (want_meta)  // IssuerMetadata string identities of this round's new certificates
+            CU(c, launch_meta_insert(c->st, sb.blob, sb.offsets, keys + lo, cnt, wu + lo, so.issuer_name_off, so.issuer_name_len,
+                                     so.crldp_off, so.crldp_len, c->meta_scratch + 2 * lo, sbm));
+        rc = peer_barrier(c, CH_DEV_RESOLVE, sbm);  // ... and their first-seen candidates in the owners' pair tables
+        if (rc) return rc;
+        CU(c, launch_resolve_pairs(c->st, keys + lo, cnt, c->pair_scratch + lo, wu + lo, fi + lo, sbm));
+        if (want_meta)
+            CU(c, launch_meta_resolve(c->st, keys + lo, cnt, c->meta_scratch + 2 * lo, o->first_issuer_dn ? o->first_issuer_dn + lo : nullptr,
+                                      o->first_crldp ? o->first_crldp + lo : nullptr, sbm));
         CU(c, cudaEventRecord(c->ev_red1[k], c->stream_b));
     }
     c->last_sub = nsub;
@@ -885,14 +848,20 @@ int ctmr_reset_device(ctmr_ctx* c, void* stream) {
     if (!c) return CTMR_E_INVALID;
     CU(c, cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    // multi-process group: collective.  Nobody may still be inserting into this shard when it is cleared, and nobody
+    // may insert into it again before it has been cleared.
+    int rc = peer_barrier(c, CH_RESET_A, s);
+    if (rc) return rc;
     CU(c, cudaMemsetAsync(c->st.table, 0, (c->st.table_mask + 1) * sizeof(KnownSlot), s));
     CU(c, cudaMemsetAsync(c->st.pairs, 0, (c->st.pair_mask + 1) * sizeof(PairSlot), s));
     CU(c, cudaMemsetAsync(c->st.meta, 0, (c->st.meta_mask + 1) * sizeof(MetaSlot), s));
     CU(c, cudaMemsetAsync(c->st.issuer_counts, 0, c->st.max_issuers * sizeof(unsigned long long), s));
+    CU(c, cudaMemsetAsync(c->st.status_counts, 0, CTMR_ST__COUNT * sizeof(unsigned long long), s));
     CU(c, cudaMemsetAsync(c->small_dev + 64, 0, 16 * sizeof(unsigned long long), s));
-    return CTMR_OK;
+    return peer_barrier(c, CH_RESET_B, s);
 }
 
+// Reads AND clears the sticky device-side failure flag: one failed batch does not poison the ctx.
 int ctmr_check_device(ctmr_ctx* c, void* stream) {
     if (!c) return CTMR_E_INVALID;
     CU(c, cudaSetDevice(c->device));
@@ -900,206 +869,84 @@ int ctmr_check_device(ctmr_ctx* c, void* stream) {
     int flag = 0;
     CU(c, cudaMemcpyAsync(&flag, c->st.error_flag, sizeof flag, cudaMemcpyDeviceToHost, s));
     CU(c, cudaStreamSynchronize(s));
-    if (flag == CTMR_E_TABLE_FULL) return fail(c, CTMR_E_TABLE_FULL, "known-certificate table is full; raise config.table_capacity");
-    if (flag) return fail(c, CTMR_E_CUDA, "device-side failure flag set");
-    return CTMR_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ the host-buffer batch
-static int process_batch_impl(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint64_t n, const uint8_t* issuer_blob,
-                              const uint64_t* issuer_offsets, uint32_t n_issuers, const uint32_t* issuer_idx, int64_t now_unix_ns,
-                              ctmr_out* out);
-
-int ctmr_process_batch(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint64_t n, const uint8_t* issuer_blob,
-                       const uint64_t* issuer_offsets, uint32_t n_issuers, const uint32_t* issuer_idx, int64_t now_unix_ns,
-                       ctmr_out* out) {
-    const int rc = process_batch_impl(c, blob, offsets, n, issuer_blob, issuer_offsets, n_issuers, issuer_idx, now_unix_ns, out);
-    if (rc != CTMR_OK && c && c->stages_ready) {  // no copy from / into the caller's buffers may outlive a failed call
-        const std::string keep = c->err;
-        for (Stage& s : c->stages) cudaStreamSynchronize(s.stream);
-        c->err = keep;
+    if (!flag) return CTMR_OK;
+    CU(c, cudaMemsetAsync(c->st.error_flag, 0, sizeof(int), s));
+    CU(c, cudaStreamSynchronize(s));
+    switch (flag) {
+    case CTMR_E_TABLE_FULL: return fail(c, flag, "known-certificate table is full; raise config.table_capacity");
+    case CTMR_E_PAIR_TABLE_FULL: return fail(c, flag, "(issuer, expDate) table is full; raise config.pair_capacity_log2");
+    case CTMR_E_META_TABLE_FULL: return fail(c, flag, "IssuerMetadata string-identity table is full; raise config.meta_capacity_log2");
+    case CTMR_E_TOO_MANY_ISSUERS: return fail(c, flag, "more distinct issuers than config.max_issuers");
+    case CTMR_E_PEER_TIMEOUT: return fail(c, flag, "a rank of the group did not reach a barrier in time (peer failed, or the collective calls diverged; CTMR_PEER_TIMEOUT_MS)");
+    default: return fail(c, CTMR_E_CUDA, "device-side failure flag set");
     }
-    return rc;
-}
-
-static int process_batch_impl(ctmr_ctx* c, const uint8_t* blob, const uint64_t* offsets, uint64_t n, const uint8_t* issuer_blob,
-                              const uint64_t* issuer_offsets, uint32_t n_issuers, const uint32_t* issuer_idx, int64_t now_unix_ns,
-                              ctmr_out* out) {
-    if (!c || !out || (n && (!blob || !offsets))) return fail(c, CTMR_E_INVALID, "bad argument");
-    if (n == 0) return CTMR_OK;
-    CU(c, cudaSetDevice(c->device));
-    int rc = ensure_stages(c);
-    if (rc) return rc;
-    // issuers of this batch -> dense indices (GPU work only for certificates never seen before)
-    const uint32_t* map_dev = nullptr;
-    if (n_issuers) {
-        std::vector<uint32_t> dense(n_issuers);
-        rc = ctmr_register_issuers(c, issuer_blob, issuer_offsets, n_issuers, dense.data());
-        if (rc) return rc;
-        if (n_issuers > c->issuer_map_cap) {
-            cudaFree(c->issuer_map_dev);
-            c->issuer_map_dev = nullptr;
-            c->issuer_map_cap = 0;
-            CU(c, cudaMalloc(&c->issuer_map_dev, (size_t)n_issuers * sizeof(uint32_t)));
-            c->issuer_map_cap = n_issuers;
-        }
-        CU(c, cudaMemcpyAsync(c->issuer_map_dev, dense.data(), n_issuers * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        map_dev = c->issuer_map_dev;
-    }
-    // pipeline: stage k = sub-batch k mod 3; H2D, map, insert, resolve, D2H each on the stage's stream.
-    // Sub-batch s+1 may only start inserting once s has resolved (lowest-index-wins needs every
-    // earlier entry in the table), expressed with one event per stage.
-    uint64_t lo = 0;
-    int sub = 0;
-    cudaEvent_t prev = nullptr;
-    const bool want_pem = out->pem != nullptr || out->pem_off != nullptr;
-    if (want_pem && !(out->pem && out->pem_off)) return fail(c, CTMR_E_INVALID, "pem and pem_off go together");
-    uint64_t pem_base = 0;
-    while (lo < n) {
-        uint64_t hi = lo + c->stage_entries < n ? lo + c->stage_entries : n;
-        if (offsets[hi] - offsets[lo] > c->stage_bytes) {  // shrink to the byte budget
-            uint64_t a = lo, b = hi;                        // largest hi with bytes <= budget
-            while (a + 1 < b) {
-                uint64_t mid = (a + b) / 2;
-                if (offsets[mid] - offsets[lo] <= c->stage_bytes) a = mid; else b = mid;
-            }
-            hi = a;
-            if (hi == lo) return fail(c, CTMR_E_BATCH_TOO_LARGE, "a single entry exceeds the staging budget (config.max_batch_bytes)");
-        }
-        Stage& s = c->stages[sub % kStages];
-        const uint64_t cnt = hi - lo, bytes = offsets[hi] - offsets[lo];
-        CU(c, cudaMemcpyAsync(s.blob, blob + offsets[lo], bytes, cudaMemcpyHostToDevice, s.stream));
-        CU(c, cudaMemcpyAsync(s.offsets, offsets + lo, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
-        if (issuer_idx) CU(c, cudaMemcpyAsync(s.issuer_idx, issuer_idx + lo, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
-        ctmr_dev_batch db{};
-        db.blob = s.blob - offsets[lo];  // offsets stay absolute
-        db.blob_bytes = offsets[hi];
-        db.offsets = s.offsets;
-        db.n = cnt;
-        db.issuer_idx = issuer_idx ? s.issuer_idx : nullptr;
-        db.issuer_map = map_dev;
-        db.issuer_map_len = n_issuers;
-        db.first_index = c->next_index + lo;
-        db.now_unix_ns = now_unix_ns;
-        ctmr_dev_out dout{};
-        dout.status = s.status;
-        dout.sha256 = out->sha256 ? s.sha : nullptr;
-        dout.exp_hour = s.exp_hour;
-        dout.serial_off = s.serial_off;
-        dout.serial_len = s.serial_len;
-        dout.keys = s.keys;
-        const bool want_meta = out->first_issuer_dn || out->first_crldp || out->issuer_name_off || out->crldp_off;
-        const uint64_t E = c->stage_entries;
-        if (want_meta) {
-            dout.issuer_name_off = s.spans;
-            dout.issuer_name_len = s.spans + E;
-            dout.crldp_off = s.spans + 2 * E;
-            dout.crldp_len = s.spans + 3 * E;
-        }
-        MapParams p;
-        fill_map_params(c, &db, &dout, p, sub % kStages, c->fuse_insert ? s.slot_of : nullptr);
-        if (c->bucket_by_length && cnt > 64 && p.sha256) {
-            CU(c, launch_len_order(s.offsets, nullptr, cnt, db.blob_bytes, s.len_hist, s.order, s.stream));
-            p.order = s.order;
-        }
-        CU(c, launch_map(p, c->sm_count, s.stream));
-        // inserts commute (atomicMax on ~index); only RESOLVE must see every earlier entry inserted
-        if (!c->fuse_insert) CU(c, launch_insert(c->st, s.keys, cnt, s.slot_of, s.stream));
-        if (prev) CU(c, cudaStreamWaitEvent(s.stream, prev, 0));
-        CU(c, launch_resolve(c->st, s.keys, cnt, s.slot_of, s.pair_slot, s.was_unknown, s.stream));
-        CU(c, cudaEventRecord(s.reduced, s.stream));
-        prev = s.reduced;
-        CU(c, launch_resolve_pairs(c->st, s.keys, cnt, s.pair_slot, s.was_unknown, s.first, s.stream));
-        if (want_meta) {
-            CU(c, launch_meta(c->st, db.blob, s.offsets, s.keys, cnt, s.was_unknown, dout.issuer_name_off, dout.issuer_name_len,
-                              dout.crldp_off, dout.crldp_len, s.meta_slots, s.first_meta, s.first_meta + E, s.stream));
-            if (out->issuer_name_off) CU(c, cudaMemcpyAsync(out->issuer_name_off + lo, dout.issuer_name_off, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
-            if (out->issuer_name_len) CU(c, cudaMemcpyAsync(out->issuer_name_len + lo, dout.issuer_name_len, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
-            if (out->crldp_off) CU(c, cudaMemcpyAsync(out->crldp_off + lo, dout.crldp_off, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
-            if (out->crldp_len) CU(c, cudaMemcpyAsync(out->crldp_len + lo, dout.crldp_len, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
-            if (out->first_issuer_dn) CU(c, cudaMemcpyAsync(out->first_issuer_dn + lo, s.first_meta, cnt, cudaMemcpyDeviceToHost, s.stream));
-            if (out->first_crldp) CU(c, cudaMemcpyAsync(out->first_crldp + lo, s.first_meta + E, cnt, cudaMemcpyDeviceToHost, s.stream));
-        }
-        if (out->status) CU(c, cudaMemcpyAsync(out->status + lo, s.status, cnt, cudaMemcpyDeviceToHost, s.stream));
-        if (out->sha256) CU(c, cudaMemcpyAsync(out->sha256 + lo * 32, s.sha, cnt * 32, cudaMemcpyDeviceToHost, s.stream));
-        if (out->exp_hour) CU(c, cudaMemcpyAsync(out->exp_hour + lo, s.exp_hour, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
-        if (out->serial_off) CU(c, cudaMemcpyAsync(out->serial_off + lo, s.serial_off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
-        if (out->serial_len) CU(c, cudaMemcpyAsync(out->serial_len + lo, s.serial_len, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
-        if (out->was_unknown) CU(c, cudaMemcpyAsync(out->was_unknown + lo, s.was_unknown, cnt, cudaMemcpyDeviceToHost, s.stream));
-        if (out->first_issuer_hour) CU(c, cudaMemcpyAsync(out->first_issuer_hour + lo, s.first, cnt, cudaMemcpyDeviceToHost, s.stream));
-        if (want_pem) {  // StoreCertificatePEM's argument for this slice's new certificates (the host waits for this slice here)
-            rc = pem_ensure(c, s.pem, c->stage_entries, c->stage_bytes);
-            if (rc) return rc;
-            rc = pem_chunk(c, s.pem, db.blob, s.offsets, nullptr, s.was_unknown, cnt, out, lo, &pem_base, s.stream);
-            if (rc) return rc;
-        }
-        lo = hi;
-        ++sub;
-    }
-    for (int k = 0; k < kStages && k < sub; ++k) CU(c, cudaStreamSynchronize(c->stages[k].stream));
-    if (want_pem) out->pem_off[n] = pem_base;
-    c->next_index += n;
-    // pairs of stage s read the pair table after resolve(s); a later stage's resolve only ever
-    // raises inv_first for lower indices, which cannot exist: indices grow with the stage number.
-    return ctmr_check_device(c, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ warm start / checkpoint
-int ctmr_preload_known(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], const uint8_t* serial_blob,
-                       const uint64_t* serial_offsets, uint64_t n) {
-    if (!c || !digest || (n && (!serial_blob || !serial_offsets))) return fail(c, CTMR_E_INVALID, "bad argument");
+}  // extern "C"
+
+namespace ctmr_host {
+// Seeds keys with the indices first_index .. first_index + n - 1 (the caller keeps them below every later batch
+// index).  Inserts go to the set's owner, so in a group any member can run it; not collective: the group is quiescent.
+int preload_impl(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], const uint8_t* serial_blob, const uint64_t* serial_offsets,
+                 uint64_t n, uint64_t first_index) {
     if (exp_hour > INT32_MAX || exp_hour < INT32_MIN) return fail(c, CTMR_E_INVALID, "exp_hour out of range");
     CU(c, cudaSetDevice(c->device));
-    // the issuer may be unknown to this ctx (state written by an earlier process): register its digest
-    std::string dk(reinterpret_cast<const char*>(digest), 32);
-    uint32_t issuer;
-    auto it = c->issuer_by_digest.find(dk);
-    if (it != c->issuer_by_digest.end()) {
-        issuer = it->second;
-    } else {
-        if (c->digests.size() >= c->st.max_issuers) return fail(c, CTMR_E_TOO_MANY_ISSUERS, "more distinct issuers than config.max_issuers");
-        issuer = (uint32_t)c->digests.size();
-        std::array<uint8_t, 32> a;
-        std::memcpy(a.data(), digest, 32);
-        c->digests.push_back(a);
-        c->issuer_by_digest.emplace(std::move(dk), issuer);
-    }
+    uint32_t issuer = 0;
+    bool found = false;
+    int rc = lookup_digest(c, digest, true, &issuer, &found);  // the issuer may be unknown so far (state written by an earlier process)
+    if (rc) return rc;
     if (!n) return CTMR_OK;
-    // key records with index 0 .. n-1 BELOW every batch index: preloaded keys always win "first seen".
-    // Batch indices are shifted up by the number of preloaded keys (next_index).
     std::vector<ctmr_key> keys(n);
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t len = serial_offsets[i + 1] - serial_offsets[i];
         if (serial_offsets[i + 1] < serial_offsets[i] || len == 0 || len > CTMR_MAX_SERIAL)
             return fail(c, CTMR_E_INVALID, "preloaded serial empty or longer than CTMR_MAX_SERIAL");
         std::memset(&keys[i], 0, sizeof(ctmr_key));
-        keys[i].index = c->next_index + i;
+        keys[i].index = first_index + i;
         keys[i].exp_hour = (int32_t)exp_hour;
         keys[i].issuer = issuer;
         keys[i].serial_len = (uint8_t)len;
         std::memcpy(keys[i].serial, serial_blob + serial_offsets[i], len);
         keys[i].valid = 1;
     }
-    int rc = ensure_scratch(c, n);
+    rc = ensure_scratch(c, n);
     if (rc) return rc;
     CU(c, cudaMemcpyAsync(c->keys_scratch, keys.data(), n * sizeof(ctmr_key), cudaMemcpyHostToDevice, c->stream));
     rc = reduce_on(c, c->keys_scratch, n, c->slot_scratch, c->pair_scratch, c->bits_scratch, c->bits_scratch + n, c->stream);
     if (rc) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
-    c->next_index += n;
     return ctmr_check_device(c, nullptr);
+}
+}  // namespace ctmr_host
+
+extern "C" {
+
+int ctmr_preload_known(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], const uint8_t* serial_blob,
+                       const uint64_t* serial_offsets, uint64_t n) {
+    if (!c || !digest || (n && (!serial_blob || !serial_offsets))) return fail(c, CTMR_E_INVALID, "bad argument");
+    if (c->group) return fail(c, CTMR_E_INVALID, "member of a group: use ctmr_group_preload_known");
+    // key records with the indices next_index .. BELOW every later batch index: preloaded keys always win "first seen"
+    int rc = preload_impl(c, exp_hour, digest, serial_blob, serial_offsets, n, c->next_index);
+    if (rc == CTMR_OK) c->next_index += n;
+    return rc;
 }
 
 namespace {
 struct SnapHeader {
-    char magic[8];  // "CTMRSNP2"
+    char magic[8];  // "CTMRSNP3"
     uint64_t table_slots, pair_slots, meta_slots, max_issuers, n_issuers, next_index;
 };
 }  // namespace
 
 int ctmr_snapshot_size(ctmr_ctx* c, uint64_t* bytes) {
     if (!c || !bytes) return fail(c, CTMR_E_INVALID, "bad argument");
+    if (c->st.peer.world > 1) return fail(c, CTMR_E_INVALID, "snapshots are per single-GPU ctx (a group's shards reference each other's issuer registry)");
+    CU(c, cudaSetDevice(c->device));
+    {
+        int rc0 = refresh_digests(c);
+        if (rc0) return rc0;
+    }
     *bytes = sizeof(SnapHeader) + (c->st.table_mask + 1) * sizeof(KnownSlot) + (c->st.pair_mask + 1) * sizeof(PairSlot) +
              (c->st.meta_mask + 1) * sizeof(MetaSlot) +
              c->st.max_issuers * sizeof(uint64_t) + CTMR_ST__COUNT * sizeof(uint64_t) + c->digests.size() * 32;
@@ -1114,7 +961,7 @@ int ctmr_snapshot_save(ctmr_ctx* c, uint8_t* buf, uint64_t cap, uint64_t* writte
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaDeviceSynchronize());
     SnapHeader h{};
-    std::memcpy(h.magic, "CTMRSNP2", 8);
+    std::memcpy(h.magic, "CTMRSNP3", 8);
     h.table_slots = c->st.table_mask + 1;
     h.pair_slots = c->st.pair_mask + 1;
     h.meta_slots = c->st.meta_mask + 1;
@@ -1137,13 +984,14 @@ int ctmr_snapshot_load(ctmr_ctx* c, const uint8_t* buf, uint64_t bytes) {
     if (!c || !buf || bytes < sizeof(SnapHeader)) return fail(c, CTMR_E_INVALID, "bad snapshot");
     SnapHeader h;
     std::memcpy(&h, buf, sizeof h);
-    if (std::memcmp(h.magic, "CTMRSNP2", 8) != 0) return fail(c, CTMR_E_INVALID, "not a ctmr snapshot");
+    if (std::memcmp(h.magic, "CTMRSNP3", 8) != 0) return fail(c, CTMR_E_INVALID, "not a ctmr snapshot");
     if (h.table_slots != c->st.table_mask + 1 || h.pair_slots != c->st.pair_mask + 1 || h.meta_slots != c->st.meta_mask + 1 ||
         h.max_issuers != c->st.max_issuers)
         return fail(c, CTMR_E_INVALID, "snapshot was taken with different capacities (table / pairs / max_issuers)");
     const uint64_t need = sizeof h + h.table_slots * sizeof(KnownSlot) + h.pair_slots * sizeof(PairSlot) +
                           h.meta_slots * sizeof(MetaSlot) + h.max_issuers * sizeof(uint64_t) + CTMR_ST__COUNT * sizeof(uint64_t) + h.n_issuers * 32;
     if (bytes < need || h.n_issuers > h.max_issuers) return fail(c, CTMR_E_INVALID, "truncated snapshot");
+    if (c->st.peer.world > 1) return fail(c, CTMR_E_INVALID, "snapshots are per single-GPU ctx");
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaDeviceSynchronize());
     const uint8_t* p = buf + sizeof h;
@@ -1156,15 +1004,28 @@ int ctmr_snapshot_load(ctmr_ctx* c, const uint8_t* buf, uint64_t bytes) {
     c->issuer_by_digest.clear();
     c->issuer_by_der.clear();  // DER memo is rebuilt lazily; dense indices come from the digests
     if (c->fe) fe_clear_issuers(c);
-    for (uint64_t i = 0; i < h.n_issuers; ++i) {
-        std::array<uint8_t, 32> a;
-        std::memcpy(a.data(), p, 32);
-        c->digests.push_back(a);
-        c->issuer_by_digest.emplace(std::string(reinterpret_cast<const char*>(p), 32), (uint32_t)i);
-        p += 32;
+    // the device registry again, digest i at index i: cleared, then filled one digest per launch (the counter hands out
+    // the indices in launch order; restores are rare and there are O(thousands) of issuers)
+    CU(c, cudaMemsetAsync(c->reg.slots, 0, (c->reg.mask + 1) * sizeof(IssuerRegSlot), c->stream));
+    CU(c, cudaMemsetAsync(c->reg.by_index, 0, (size_t)c->reg.max_issuers * 32, c->stream));
+    CU(c, cudaMemsetAsync(c->reg.counter, 0, sizeof(unsigned long long), c->stream));
+    if (h.n_issuers) {
+        uint8_t* d_dig = nullptr;
+        uint32_t* d_idx = nullptr;
+        CU(c, cudaMalloc(&d_dig, h.n_issuers * 32));
+        CU(c, cudaMalloc(&d_idx, h.n_issuers * sizeof(uint32_t)));
+        CU(c, cudaMemcpyAsync(d_dig, p, h.n_issuers * 32, cudaMemcpyHostToDevice, c->stream));
+        for (uint64_t i = 0; i < h.n_issuers; ++i)
+            CU(c, launch_issuer_registry(c->reg, d_dig + 32 * i, nullptr, 1, d_idx + i, c->st.error_flag, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(d_dig);
+        cudaFree(d_idx);
     }
     c->next_index = h.next_index;
-    return CTMR_OK;
+    int rc = refresh_digests(c);
+    if (rc) return rc;
+    if (c->digests.size() != h.n_issuers) return fail(c, CTMR_E_INVALID, "snapshot holds duplicate issuer digests");
+    return ctmr_check_device(c, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ tooling
@@ -1194,6 +1055,10 @@ int ctmr_sha256_ceiling_device(ctmr_ctx* c, uint32_t iters, uint32_t rolled, uin
 int ctmr_issuer_counts(ctmr_ctx* c, uint8_t* digests, uint64_t* counts, size_t* n) {
     if (!c || !n) return fail(c, CTMR_E_INVALID, "bad argument");
     CU(c, cudaSetDevice(c->device));
+    {
+        int rc0 = refresh_digests(c);  // issuers another rank of the group registered count too (with 0 here)
+        if (rc0) return rc0;
+    }
     const size_t have = c->digests.size(), cap = *n;
     const size_t take = have < cap ? have : cap;
     if (take) {
@@ -1212,10 +1077,13 @@ int ctmr_set_cardinality(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32]
     if (!c || !digest || !out) return fail(c, CTMR_E_INVALID, "bad argument");
     CU(c, cudaSetDevice(c->device));
     *out = 0;
-    auto it = c->issuer_by_digest.find(std::string(reinterpret_cast<const char*>(digest), 32));
-    if (it == c->issuer_by_digest.end() || exp_hour > INT32_MAX || exp_hour < INT32_MIN) return CTMR_OK;
-    CU(c, cudaMemsetAsync(c->small_dev + 80, 0, sizeof(unsigned long long), c->stream));
-    CU(c, launch_cardinality(c->st, (int32_t)exp_hour, it->second, c->small_dev + 80, c->stream));
+    uint32_t issuer = 0;
+    bool found = false;
+    int rc = lookup_digest(c, digest, false, &issuer, &found);
+    if (rc) return rc;
+    if (!found || exp_hour > INT32_MAX || exp_hour < INT32_MIN) return CTMR_OK;
+    // one probe of the set's (issuer, hour) slot at its owner -- which may be another GPU of the group
+    CU(c, launch_cardinality(c->st, (int32_t)exp_hour, issuer, c->small_dev + 80, c->stream));
     unsigned long long v = 0;
     CU(c, cudaMemcpyAsync(&v, c->small_dev + 80, sizeof v, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -1258,6 +1126,7 @@ int ctmr_evict_expired(ctmr_ctx* c, int64_t now_unix_sec, uint64_t* evicted_out)
     CU(c, cudaStreamSynchronize(c->stream));
     if (evicted_out) *evicted_out = counters[1];
     if (counters[1] == 0) return CTMR_OK;
+    CU(c, launch_evict_pairs(c->st, now_unix_sec, c->stream));  // the expired sets' cardinalities are 0 again
     // open addressing with linear probing: taking slots out would cut probe chains, so the survivors are
     // compacted aside, the table is cleared and they are inserted again (first-seen indices preserved)
     KnownSlot* keep = nullptr;

@@ -65,9 +65,42 @@ __device__ __forceinline__ uint64_t key_hash(const uint32_t (&b)[12]) {
     return h;
 }
 
-// Find-or-insert of a 48-byte key body; lowest global index wins through atomicMax on ~index.
-// Returns the slot, or 0xFFFFFFFF when the table is full (error flag set).  Shared by K_insert
-// and by K_map when the insert is fused into the map kernel (single-GPU path).
+// Scope of the table atomics: device scope on a single GPU, system scope once peers' tables are addressed
+// over NVLink (the atomic is performed at the owner's L2 either way; the scope decides what it is ordered with).
+template <bool SYS>
+__device__ __forceinline__ unsigned long long tab_cas(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
+    return SYS ? atomicCAS_system(p, cmp, v) : atomicCAS(p, cmp, v);
+}
+template <bool SYS>
+__device__ __forceinline__ void tab_max(unsigned long long* p, unsigned long long v) {
+    if (SYS) asm volatile("red.relaxed.sys.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    else asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+template <bool SYS>
+__device__ __forceinline__ void tab_add(unsigned long long* p, unsigned long long v) {
+    if (SYS) asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    else asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+template <bool SYS>
+__device__ __forceinline__ void tab_store_release(unsigned long long* p, unsigned long long v) {
+    if (SYS) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    else asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+template <bool SYS>
+__device__ __forceinline__ unsigned long long tab_load_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    if (SYS) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// 16 bytes of a slot that another GPU may have written: never from a stale L1 line
+__device__ __forceinline__ uint4 ld_cv_u4(const uint4* p) { return __ldcv(p); }
+
+// Find-or-insert of a 48-byte key body in the OWNER's table (possibly another GPU's, over NVLink); lowest global
+// index wins through an atomic max on ~index.  One round trip claims an empty slot (optimistic CAS: the tag read
+// is the CAS's return value), the key bytes and the ready tag follow as posted writes (release store).  Returns
+// the slot, or 0xFFFFFFFF when the table is full (error flag set).  Shared by K_insert and by K_map's fused insert.
+template <bool SYS>
 __device__ __forceinline__ uint32_t known_insert(KnownSlot* __restrict__ table, uint64_t table_mask, int* error_flag,
                                                  const uint32_t (&body)[12], unsigned long long inv_idx) {
     const uint64_t h = key_hash(body);
@@ -76,30 +109,25 @@ __device__ __forceinline__ uint32_t known_insert(KnownSlot* __restrict__ table, 
     uint32_t probes = 0;
     for (;;) {
         KnownSlot* sl = table + pos;
-        unsigned long long t = ld_volatile_u64(&sl->tag);
-        if (t == 0ull) {
-            t = atomicCAS(&sl->tag, 0ull, tag_pending);
-            if (t == 0ull) {  // claimed: publish the key bytes, then flip to ready
-                uint4* bp = reinterpret_cast<uint4*>(sl->body);
-                bp[0] = make_uint4(body[0], body[1], body[2], body[3]);
-                bp[1] = make_uint4(body[4], body[5], body[6], body[7]);
-                bp[2] = make_uint4(body[8], body[9], body[10], body[11]);
-                __threadfence();
-                atomicExch(&sl->tag, tag_ready);
-                atomicMax(&sl->inv_first, inv_idx);
-                return (uint32_t)pos;
-            }
+        unsigned long long t = tab_cas<SYS>(&sl->tag, 0ull, tag_pending);
+        if (t == 0ull) {  // claimed: publish the key bytes, then flip to ready
+            uint4* bp = reinterpret_cast<uint4*>(sl->body);
+            bp[0] = make_uint4(body[0], body[1], body[2], body[3]);
+            bp[1] = make_uint4(body[4], body[5], body[6], body[7]);
+            bp[2] = make_uint4(body[8], body[9], body[10], body[11]);
+            tab_store_release<SYS>(&sl->tag, tag_ready);
+            tab_max<SYS>(&sl->inv_first, inv_idx);
+            return (uint32_t)pos;
         }
         if ((t & ~3ull) == (h & ~3ull)) {
-            if ((t & 3ull) == 1ull) continue;  // another thread is publishing this slot: look again
-            __threadfence();
+            while ((t & 3ull) == 1ull) t = tab_load_acquire<SYS>(&sl->tag);  // another thread is publishing this slot
             const uint4* bp = reinterpret_cast<const uint4*>(sl->body);
-            const uint4 b0 = bp[0], b1 = bp[1], b2 = bp[2];
+            const uint4 b0 = ld_cv_u4(bp), b1 = ld_cv_u4(bp + 1), b2 = ld_cv_u4(bp + 2);
             const bool same = b0.x == body[0] && b0.y == body[1] && b0.z == body[2] && b0.w == body[3] && b1.x == body[4] &&
                               b1.y == body[5] && b1.z == body[6] && b1.w == body[7] && b2.x == body[8] && b2.y == body[9] &&
                               b2.z == body[10] && b2.w == body[11];
             if (same) {
-                atomicMax(&sl->inv_first, inv_idx);
+                tab_max<SYS>(&sl->inv_first, inv_idx);
                 return (uint32_t)pos;
             }
         }
@@ -109,6 +137,13 @@ __device__ __forceinline__ uint32_t known_insert(KnownSlot* __restrict__ table, 
             return 0xFFFFFFFFu;
         }
     }
+}
+
+// owner dispatch: the key (exp_hour, issuer) picks the GPU whose table holds the set
+__device__ __forceinline__ uint32_t known_insert_owner(KnownSlot* const* tables, uint32_t world, uint64_t table_mask, int* error_flag,
+                                                       const uint32_t (&body)[12], unsigned long long inv_idx) {
+    if (world <= 1u) return known_insert<false>(tables[0], table_mask, error_flag, body, inv_idx);
+    return known_insert<true>(tables[key_owner((int32_t)body[0], body[1], world)], table_mask, error_flag, body, inv_idx);
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {

@@ -27,10 +27,14 @@ struct __align__(16) KnownSlot {
 };
 static_assert(sizeof(KnownSlot) == 64, "KnownSlot layout");
 
-struct __align__(16) PairSlot {
+struct __align__(16) PairSlot {   // one per Redis set "serials::<expDate>::<issuer>" ever written
     unsigned long long key;        // ((issuer << 32) | (uint32)exp_hour) + 1; 0 = empty
     unsigned long long inv_first;  // ~(lowest index among was-unknown entries of this (issuer, hour))
+    unsigned long long count;      // SetCardinality of the set: unique serials inserted and not yet expired
+    unsigned long long pad;
 };
+static_assert(sizeof(PairSlot) == 32, "PairSlot layout");
+
 
 struct __align__(16) MetaSlot {      // IssuerMetadata string sets: identity = two independent 64-bit hashes
     unsigned long long h1;           // 0 = empty
@@ -39,11 +43,57 @@ struct __align__(16) MetaSlot {      // IssuerMetadata string sets: identity = t
     unsigned long long pad;
 };
 
+// Multi-GPU: every set "serials::<expDate>::<issuer>" has ONE owner GPU
+// (key_owner(exp_hour, issuer, world)), which holds its serials, its (issuer, hour) slot and -- by the hash of
+// the string -- the IssuerMetadata identities.  The owners' tables are mapped into every rank (peer access in one
+// process, CUDA IPC across processes) and the kernels address them directly over NVLink: slot claims are
+// system-scope atomicCAS, lowest-index-wins is a system-scope atomicMax, results are read back after a barrier.
+constexpr uint32_t kMaxWorld = 8;
+
+struct PeerTables {
+    KnownSlot* table[kMaxWorld];
+    PairSlot* pairs[kMaxWorld];
+    MetaSlot* meta[kMaxWorld];
+    uint32_t world;  // 1 = single GPU: device-scope atomics, no peer traffic
+    uint32_t rank;
+};
+
+// ctx-lifetime issuer registry ON THE DEVICE of rank 0: Issuer.ID digest -> dense index, find-or-insert with
+// system-scope atomics, so that every rank of a group gets the same index for the same issuer without any host
+// coordination (a key record carries the dense index; owner routing and the full-key compare depend on it).
+struct __align__(16) IssuerRegSlot {
+    unsigned long long state;  // 0 empty | 1 pending | 2 ready
+    uint32_t idx;
+    uint32_t pad;
+    uint8_t digest[32];
+    unsigned long long pad2[2];
+};
+static_assert(sizeof(IssuerRegSlot) == 64, "IssuerRegSlot layout");
+
+struct IssuerRegistry {
+    IssuerRegSlot* slots;          // [mask + 1]
+    uint64_t mask;
+    unsigned long long* counter;   // number of dense indices handed out
+    uint8_t* by_index;             // [max_issuers][32]
+    uint32_t max_issuers;
+};
+
+// barrier flags and histograms of every rank, for the cross-process barrier and the one-shot all-reduce
+struct PeerFlags {
+    unsigned long long* flags[kMaxWorld];          // [kPeerChannels][kMaxWorld] epochs, written by the peers
+    unsigned long long* issuer_counts[kMaxWorld];  // [max_issuers]
+    unsigned long long* status_counts[kMaxWorld];  // [CTMR_ST__COUNT]
+    uint32_t world, rank;
+    unsigned long long timeout_ns;                 // a barrier wait longer than this raises CTMR_E_PEER_TIMEOUT
+};
+constexpr uint32_t kPeerChannels = 16;
+
 struct DeviceState {
-    KnownSlot* table;
-    uint64_t table_mask;       // capacity - 1
+    KnownSlot* table;          // this rank's shard (== peer.table[peer.rank])
+    uint64_t table_mask;       // capacity - 1, identical on every rank
     PairSlot* pairs;
     uint64_t pair_mask;
+    PeerTables peer;
     unsigned long long* issuer_counts;  // [max_issuers]
     uint32_t max_issuers;
     unsigned long long* status_counts;  // [CTMR_ST__COUNT]
@@ -81,8 +131,10 @@ struct MapParams {
     unsigned long long* status_counts;
     unsigned long long* work_counter;  // [1] scratch of the dynamically scheduled map kernel
     const uint32_t* order;             // [n] length-bucketed processing order (NULL = entry order)
-    // fused K_insert (slot_of != NULL): the known-certificate table and where each entry's slot goes
-    KnownSlot* table;
+    // fused K_insert (slot_of != NULL): the owners' known-certificate tables and where each entry's slot goes
+    KnownSlot* table[kMaxWorld];
+    uint32_t world;
+    uint32_t pad_world;
     uint64_t table_mask;
     int* error_flag;
     uint32_t* slot_of;
@@ -104,6 +156,18 @@ cudaError_t launch_meta(const DeviceState& st, const uint8_t* blob, const uint64
                         const uint8_t* was_unknown, const uint32_t* name_off, const uint32_t* name_len, const uint32_t* crl_off,
                         const uint32_t* crl_len, uint32_t* meta_slots /* [2*m] scratch */, uint8_t* first_dn, uint8_t* first_crl,
                         cudaStream_t s);
+cudaError_t launch_meta_insert(const DeviceState& st, const uint8_t* blob, const uint64_t* offsets, const ctmr_key* keys, uint64_t m,
+                               const uint8_t* was_unknown, const uint32_t* name_off, const uint32_t* name_len, const uint32_t* crl_off,
+                               const uint32_t* crl_len, uint32_t* meta_slots, cudaStream_t s);
+cudaError_t launch_meta_resolve(const DeviceState& st, const ctmr_key* keys, uint64_t m, const uint32_t* meta_slots, uint8_t* first_dn,
+                                uint8_t* first_crl, cudaStream_t s);
+cudaError_t launch_evict_pairs(const DeviceState& st, int64_t now_sec, cudaStream_t s);
+cudaError_t launch_issuer_registry(const IssuerRegistry& reg, const uint8_t* digests, const uint8_t* ok, uint32_t n, uint32_t* idx_out,
+                                   int* error_flag, cudaStream_t s);
+cudaError_t launch_peer_post(const PeerFlags& pf, unsigned long long value, cudaStream_t s);
+cudaError_t launch_peer_barrier(const PeerFlags& pf, uint32_t channel, unsigned long long epoch, int* error_flag, cudaStream_t s);
+cudaError_t launch_hist_sum(const PeerFlags& pf, uint32_t n_slots, unsigned long long* counts_dst, unsigned long long* status_dst,
+                            cudaStream_t s);
 cudaError_t launch_issuer_prepare(const uint8_t* blob, const uint64_t* offsets, uint32_t n, uint8_t* digests,
                                   uint8_t* ok, cudaStream_t s);
 cudaError_t launch_table_count(const DeviceState& st, unsigned long long* out, cudaStream_t s);

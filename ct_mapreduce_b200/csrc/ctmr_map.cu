@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256, 4) map_light_kernel(const __grid_constant
             kr[1] = make_uint4(body[2], body[3], body[4], body[5]);
             kr[2] = make_uint4(body[6], body[7], body[8], body[9]);
             kr[3] = make_uint4(body[10], body[11], valid ? 1u : 0u, 0u);
-            if (p.slot_of) p.slot_of[e] = valid ? known_insert(p.table, p.table_mask, p.error_flag, body, ~gi) : 0xFFFFFFFFu;
+            if (p.slot_of) p.slot_of[e] = valid ? known_insert_owner(p.table, p.world, p.table_mask, p.error_flag, body, ~gi) : 0xFFFFFFFFu;
         }
     }
     if (p.status_counts) {
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
                         const uint2 k3 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(kr) + 12);
                         const uint32_t body[12] = {(uint32_t)(int32_t)exp_hour, issuer, k1.x, k1.y, k1.z, k1.w,
                                                    k2.x, k2.y, k2.z, k2.w, k3.x, k3.y};
-                        slot = known_insert(p.table, p.table_mask, p.error_flag, body, ~gi);
+                        slot = known_insert_owner(p.table, p.world, p.table_mask, p.error_flag, body, ~gi);
                     }
                     p.slot_of[e] = slot;
                 }
@@ -469,8 +469,8 @@ cudaError_t launch_sha_ceiling(uint32_t iters, int rolled, int ctas_per_sm, int 
     return cudaGetLastError();
 }
 
-// Shape of the persistent grid.  Defaults = the measured best (DESIGN.md "K_map tuning"); the
-// environment overrides exist for the A/B runs recorded under profiles/.
+// Shape of the persistent grid = the measured best (DESIGN.md "K_map tuning").  A build with
+// CTMR_EXPERIMENTS=1 adds the environment overrides used for the A/B runs recorded under profiles/.
 cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {
     if (p.n == 0) return cudaSuccess;
     static const int light = env_int("CTMR_MAP_LIGHT", 1);
@@ -478,37 +478,42 @@ cudaError_t launch_map(const MapParams& p, int sm_count, cudaStream_t s) {
         map_light_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, s>>>(p);
         return cudaGetLastError();
     }
+#ifdef CTMR_EXPERIMENTS  // tuning + measured-and-rejected variants: not in the product build
     static const int variant = env_int("CTMR_MAP_VARIANT", 2);   // 1: v1 (global-memory walk), 2: streaming walk
     static const int loader = env_int("CTMR_MAP_LOADER", 0);     // 0: cp.async (LDGSTS), 1: TMA bulk copy
     static const int warps = env_int("CTMR_MAP_WARPS", 8);
     static const int chunk = env_int("CTMR_MAP_CHUNK", 128);
     static const int cps = env_int("CTMR_MAP_CTAS_PER_SM", 0);
+    static const int rolled = env_int("CTMR_MAP_ROLLED", 1);
     if (variant != 2 && p.lens) return cudaErrorNotSupported;  // only the streaming kernel takes explicit lengths
     if (variant == 1) return launch_map_v1(p, sm_count, s);
     if (variant == 3) return launch_map_v3(p, sm_count, s);
-    if (loader == 1) {
-        if (chunk == 128) return launch_stream_t<4, 128, 1>(p, sm_count, cps ? cps : 4, s);
-        return launch_stream_t<4, 256, 1>(p, sm_count, cps ? cps : 2, s);
+    if (loader == 1) {  // TMA bulk-copy loader, like for like with the shipped kernel: 8 warps, 128-byte chunks, rolled SHA-256
+        if (chunk == 128 && warps == 8) return launch_stream_t<8, 128, 1, 1>(p, sm_count, cps ? cps : 2, s);
+        if (chunk == 128) return launch_stream_t<4, 128, 1, 1>(p, sm_count, cps ? cps : 4, s);
+        return launch_stream_t<4, 256, 1, 1>(p, sm_count, cps ? cps : 2, s);
     }
-    static const int rolled = env_int("CTMR_MAP_ROLLED", 1);
     if (rolled >= 2 && chunk == 128) {
         if (rolled == 2) return launch_stream_t<8, 128, 0, 2>(p, sm_count, cps ? cps : 2, s);
         if (rolled == 3) return launch_stream_t<8, 128, 0, 3>(p, sm_count, cps ? cps : 2, s);
-        return launch_stream_t<8, 128, 0, 4>(p, sm_count, cps ? cps : 2, s);
+        if (rolled == 4) return launch_stream_t<8, 128, 0, 4>(p, sm_count, cps ? cps : 2, s);
     }
     if (rolled && chunk == 64) return launch_stream_t<8, 64, 0, 1>(p, sm_count, cps ? cps : 3, s);
     if (rolled && chunk == 128 && warps == 6) return launch_stream_t<6, 128, 0, 1>(p, sm_count, cps ? cps : 3, s);
-    if (rolled) {
-        if (chunk == 128) return launch_stream_t<8, 128, 0, 1>(p, sm_count, cps ? cps : 2, s);
+    if (rolled && chunk == 256) {
         if (warps == 4) return launch_stream_t<4, 256, 0, 1>(p, sm_count, cps ? cps : 2, s);
         return launch_stream_t<8, 256, 0, 1>(p, sm_count, cps ? cps : 1, s);
     }
-    if (chunk == 128) {
-        if (warps == 8) return launch_stream_t<8, 128, 0>(p, sm_count, cps ? cps : 2, s);
-        return launch_stream_t<4, 128, 0>(p, sm_count, cps ? cps : 4, s);
+    if (!rolled) {
+        if (chunk == 128) return warps == 8 ? launch_stream_t<8, 128, 0>(p, sm_count, cps ? cps : 2, s)
+                                            : launch_stream_t<4, 128, 0>(p, sm_count, cps ? cps : 4, s);
+        return warps == 8 ? launch_stream_t<8, 256, 0>(p, sm_count, cps ? cps : 1, s) : launch_stream_t<4, 256, 0>(p, sm_count, cps ? cps : 2, s);
     }
-    if (warps == 8) return launch_stream_t<8, 256, 0>(p, sm_count, cps ? cps : 1, s);
-    return launch_stream_t<4, 256, 0>(p, sm_count, cps ? cps : 2, s);
+    return launch_stream_t<8, 128, 0, 1>(p, sm_count, cps ? cps : 2, s);
+#else
+    // the shipped shape: 8 warps x 32 lanes, 128-byte chunks, cp.async staging, rolled SHA-256, 2 CTAs per SM
+    return launch_stream_t<8, 128, 0, 1>(p, sm_count, 2, s);
+#endif
 }
 
 }  // namespace ctmr

@@ -47,7 +47,8 @@ typedef struct ctmr_synth_cfg {
     uint32_t len_mode;  /* 0: uniform in [len_lo, len_hi]; 1: octave log-uniform in [len_lo, len_hi) */
     uint32_t len_lo;
     uint32_t len_hi;
-    uint32_t dup_mode;  /* 0: all certificates distinct; 1: every certificate appears exactly twice */
+    uint32_t dup_mode;  /* 0: all certificates distinct; 1: every certificate appears exactly twice;
+                         * d >= 2: one entry in d repeats another certificate (pairs at permuted positions) */
     uint32_t reserved;
     int64_t now_sec;    /* fixed "now" (2026-01-01T00:00:00Z = 1767225600) */
 } ctmr_synth_cfg;
@@ -124,6 +125,10 @@ CTMR_HD uint64_t ctmr_synth_perm(const ctmr_synth_cfg* c, uint64_t i) {
 
 CTMR_HD uint64_t ctmr_synth_cert_id(const ctmr_synth_cfg* c, uint64_t i) {
     if (c->dup_mode == 1 && c->n_total >= 2) return ctmr_synth_perm(c, i) >> 1;
+    if (c->dup_mode >= 2 && c->n_total >= 2) {  /* positions p = d-1 (mod d) repeat the certificate of position p-1 */
+        const uint64_t p = ctmr_synth_perm(c, i);
+        return (p % c->dup_mode == c->dup_mode - 1) ? p - 1 : p;
+    }
     return i;
 }
 

@@ -94,8 +94,12 @@ class GpuCertDatabase:
 
     def __init__(self, device: int = 0, table_capacity: int = 1 << 22, issuer_cn_filter: bytes | str = b"",
                  log_expired_entries: bool = False, flags: int = 0, max_issuers: int = 0, max_batch_entries: int = 0,
-                 max_batch_bytes: int = 0, pair_capacity_log2: int = 0):
+                 max_batch_bytes: int = 0, pair_capacity_log2: int = 0, meta_capacity_log2: int = 0, _adopt=None):
         self._lib = capi.load()
+        if _adopt is not None:  # a member of a GpuCertGroup: the group owns the handle
+            self._h, self.device, self.flags, self._owned = _adopt, device, flags, False
+            return
+        self._owned = True
         if isinstance(issuer_cn_filter, str):
             issuer_cn_filter = issuer_cn_filter.encode()
         self._filter = bytes(issuer_cn_filter)
@@ -107,6 +111,7 @@ class GpuCertDatabase:
         cfg.max_batch_bytes = max_batch_bytes
         cfg.max_issuers = max_issuers
         cfg.pair_capacity_log2 = pair_capacity_log2
+        cfg.meta_capacity_log2 = meta_capacity_log2
         cfg.issuer_cn_filter = self._filter
         cfg.issuer_cn_filter_len = len(self._filter)
         cfg.log_expired_entries = int(bool(log_expired_entries))
@@ -126,7 +131,8 @@ class GpuCertDatabase:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.ctmr_destroy(self._h)
+            if getattr(self, "_owned", True):
+                self._lib.ctmr_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -189,11 +195,14 @@ class GpuCertDatabase:
                         capi.ptr(out.crldp_len), capi.ptr(out.first_issuer_dn), capi.ptr(out.first_crldp)] if want_meta else [None] * 6))
         if want_pem:
             _attach_pem(o, out, n, int(blob.size))
-        self._check(self._lib.ctmr_process_batch(self._h, capi.ptr(blob), capi.ptr(offsets), n,
-                                                 capi.ptr(issuer_blob) if n_iss else None,
-                                                 capi.ptr(issuer_offsets) if n_iss else None, n_iss,
-                                                 capi.ptr(issuer_idx), now_unix_ns, C.byref(o)))
+        self._check(self._process_batch_fn()(self._h, capi.ptr(blob), capi.ptr(offsets), n,
+                                             capi.ptr(issuer_blob) if n_iss else None,
+                                             capi.ptr(issuer_offsets) if n_iss else None, n_iss,
+                                             capi.ptr(issuer_idx), now_unix_ns, C.byref(o)))
         return out
+
+    def _process_batch_fn(self):
+        return self._lib.ctmr_process_batch
 
     # ------------------------------------------------------------------ CT wire-format front end (include/ctmr_frontend.h)
     def store_raw_entries(self, text, leaf_off, leaf_len, extra_off, extra_len, now_unix_ns: int, want_sha: bool = True,
@@ -270,6 +279,23 @@ class GpuCertDatabase:
     def check_device(self, stream=None):
         self._check(self._lib.ctmr_check_device(self._h, stream))
 
+    # ------------------------------------------------------------------ one process per GPU: peers over CUDA IPC (ctmr_peer_*)
+    def peer_export(self) -> bytes:
+        h = (C.c_uint8 * capi.PEER_HANDLE_BYTES)()
+        self._check(self._lib.ctmr_peer_export(self._h, h))
+        return bytes(h)
+
+    def peer_attach(self, rank: int, world: int, handles: list):
+        """handles[r] = rank r's peer_export().  Afterwards process_device / store_batch / reset_device are collective."""
+        buf = (C.c_uint8 * (capi.PEER_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
+        self._check(self._lib.ctmr_peer_attach(self._h, rank, world, buf))
+
+    def peer_barrier_device(self, stream=None):
+        self._check(self._lib.ctmr_peer_barrier_device(self._h, stream))
+
+    def peer_allreduce_histogram_device(self, counts_dst, n_slots: int, status_dst=None, stream=None):
+        self._check(self._lib.ctmr_peer_allreduce_histogram_device(self._h, capi.ptr(counts_dst), n_slots, capi.ptr(status_dst), stream))
+
     # ------------------------------------------------------------------ warm start / checkpoint (SURVEY §8(f)-4)
     def preload_known(self, exp_hour: int, issuer_digest: bytes, serials):
         """Seed one "serials::<expDate>::<issuer>" set (e.g. KnownCertificates.Known() read back from Redis)."""
@@ -320,6 +346,100 @@ class GpuCertDatabase:
     def table_stats(self):
         used, cap = C.c_uint64(0), C.c_uint64(0)
         self._check(self._lib.ctmr_table_stats(self._h, C.byref(used), C.byref(cap)))
+        return used.value, cap.value
+
+
+class GpuCertGroup(GpuCertDatabase):
+    """Several GPUs of one box behind ONE handle (ctmr_group_*): what the Go host calls in place of the worker pool of
+    StartDatabaseThreads (cmd/ct-fetch/ct-fetch.go:140-145).  Same methods, globally exact results: every set
+    "serials::<expDate>::<issuer>" lives on one owner GPU and the map kernels insert into it over NVLink."""
+
+    def __init__(self, devices, table_capacity: int = 1 << 22, issuer_cn_filter: bytes | str = b"", log_expired_entries: bool = False,
+                 flags: int = 0, max_issuers: int = 0, max_batch_entries: int = 0, max_batch_bytes: int = 0,
+                 pair_capacity_log2: int = 0, meta_capacity_log2: int = 0):
+        self._lib = capi.load()
+        if isinstance(issuer_cn_filter, str):
+            issuer_cn_filter = issuer_cn_filter.encode()
+        self._filter = bytes(issuer_cn_filter)
+        cfg = capi.Config()
+        cfg.struct_size = C.sizeof(capi.Config)
+        cfg.table_capacity, cfg.max_batch_entries, cfg.max_batch_bytes = table_capacity, max_batch_entries, max_batch_bytes
+        cfg.max_issuers, cfg.pair_capacity_log2, cfg.meta_capacity_log2 = max_issuers, pair_capacity_log2, meta_capacity_log2
+        cfg.issuer_cn_filter, cfg.issuer_cn_filter_len = self._filter, len(self._filter)
+        cfg.log_expired_entries, cfg.flags = int(bool(log_expired_entries)), flags
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._lib.ctmr_group_create(C.byref(cfg), devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise CtmrError(rc, (self._lib.ctmr_group_last_error(None) or b"").decode())
+        self._h, self._owned = h, True
+        self.devices, self.device, self.flags = list(devices), devices[0], flags
+        self.members = [GpuCertDatabase(device=devices[r], flags=flags, _adopt=C.c_void_p(self._lib.ctmr_group_member(h, r)))
+                        for r in range(len(devices))]
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CtmrError(rc, (self._lib.ctmr_group_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for m in self.members:
+                m._h = None
+            self._lib.ctmr_group_destroy(self._h)
+            self._h = None
+
+    def _process_batch_fn(self):
+        return self._lib.ctmr_group_process_batch
+
+    def register_issuers(self, issuer_blob, issuer_offsets):
+        return self.members[0].register_issuers(issuer_blob, issuer_offsets)   # the registry is the group's
+
+    def issuer_digest(self, dense_idx: int) -> bytes:
+        return self.members[0].issuer_digest(dense_idx)
+
+    def preload_known(self, exp_hour: int, issuer_digest: bytes, serials):
+        serials = [bytes(x) for x in serials]
+        offs = np.zeros(len(serials) + 1, np.uint64)
+        offs[1:] = np.cumsum([len(x) for x in serials], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(serials) or b"\0", np.uint8).copy()
+        d = (C.c_uint8 * 32).from_buffer_copy(issuer_digest)
+        self._check(self._lib.ctmr_group_preload_known(self._h, exp_hour, d, capi.ptr(blob), capi.ptr(offs), len(serials)))
+
+    def evict_expired(self, now_unix_sec: int) -> int:
+        n = C.c_uint64(0)
+        self._check(self._lib.ctmr_group_evict_expired(self._h, int(now_unix_sec), C.byref(n)))
+        return int(n.value)
+
+    def reset(self):
+        self._check(self._lib.ctmr_group_reset(self._h))
+
+    def get_known_certificates(self, exp_hour: int, issuer_digest: bytes):
+        grp = self
+
+        class _View:
+            def count(self_inner) -> int:
+                out = C.c_uint64(0)
+                d = (C.c_uint8 * 32).from_buffer_copy(bytes(issuer_digest))
+                grp._check(grp._lib.ctmr_group_set_cardinality(grp._h, int(exp_hour), d, C.byref(out)))
+                return out.value
+        return _View()
+
+    def issuer_counts(self) -> dict:
+        n = C.c_size_t(self._lib.ctmr_issuer_count(self.members[0]._h))
+        cap = max(int(n.value), 1)
+        dig = np.zeros((cap, 32), np.uint8)
+        cnt = np.zeros(cap, np.uint64)
+        self._check(self._lib.ctmr_group_issuer_counts(self._h, capi.ptr(dig), capi.ptr(cnt), C.byref(n)))
+        return {bytes(dig[i]): int(cnt[i]) for i in range(n.value)}
+
+    def status_counters(self) -> np.ndarray:
+        out = np.zeros(capi.ST_COUNT, np.uint64)
+        self._check(self._lib.ctmr_group_status_counters(self._h, capi.ptr(out)))
+        return out
+
+    def table_stats(self):
+        used, cap = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.ctmr_group_table_stats(self._h, C.byref(used), C.byref(cap)))
         return used.value, cap.value
 
 

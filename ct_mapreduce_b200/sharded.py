@@ -24,6 +24,59 @@ from . import capi
 KEY_BYTES = capi.KEY_BYTES
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# One process per GPU, owners' tables attached over CUDA IPC (include/ctmr.h "ctmr_peer_*"): the exact multi-GPU
+# path.  torch.distributed only carries the 128-byte handles at start-up (any backend) and the bench's timing
+# reductions; there is no collective on the data path -- K_map inserts into the owner's table over NVLink and the
+# ranks meet at barriers kept in peer memory.
+# ---------------------------------------------------------------------------------------------------------------
+def attach_peers(db, group=None):
+    """All ranks: exchange peer handles and attach.  Afterwards db.process_device / store_batch / reset_device /
+    peer_allreduce_histogram_device are collective calls (same sequence on every rank)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        return rank, world
+    handles = [None] * world
+    dist.all_gather_object(handles, db.peer_export(), group=group)
+    db.peer_attach(rank, world, handles)
+    return rank, world
+
+
+def round_entries(n: int, rounds: int = capi.PEER_ROUNDS) -> int:
+    """E of the collective ctmr_process_device: entries per rank and round (every rank passes the same n)."""
+    return -(-n // rounds)
+
+
+def call_index_span(n: int, world: int, rounds: int = capi.PEER_ROUNDS) -> int:
+    """How far a collective ctmr_process_device call advances the global index (its next call's first_index)."""
+    return world * rounds * round_entries(n, rounds)
+
+
+def sequential_order(n: int, world: int, rounds: int = capi.PEER_ROUNDS):
+    """The order in which the sequential reference (numThreads=1) would have to see the entries of one collective
+    call for its result to equal the group's: rounds in order, inside a round the ranks in order, inside a rank's
+    slice the entries in order.  Yields (rank, lo, hi) slices of each rank's local batch [0, n)."""
+    e = round_entries(n, rounds)
+    for k in range(rounds):
+        lo, hi = min(n, k * e), min(n, (k + 1) * e)
+        for r in range(world):
+            if hi > lo:
+                yield r, lo, hi
+
+
+def host_batch_order(ns, stage_entries: int):
+    """The same for the collective HOST-buffer call (ctmr_process_batch with peers attached): rank r passes ns[r]
+    entries, a round takes `stage_entries` per rank, every rank runs max(rounds) rounds.  (Byte-budget shrinking of a
+    round is not modelled: callers keep entries below config.max_batch_bytes / stage_entries on average.)"""
+    rounds = max(1, max(-(-n // stage_entries) for n in ns))
+    for k in range(rounds):
+        for r, n in enumerate(ns):
+            lo, hi = min(n, k * stage_entries), min(n, (k + 1) * stage_entries)
+            if hi > lo:
+                yield r, lo, hi
+
+
 class GpuOps:
     """The five device operations, straight onto the C ABI (no arithmetic in Python)."""
 

@@ -23,6 +23,10 @@
  *     past return (cgo rule).  Device state lives in an opaque ctmr_ctx.
  *   - one ctmr_ctx per GPU, calls on a ctx are serialised by the caller; batches are ordered:
  *     every entry of call k precedes every entry of call k+1 for first-seen semantics.
+ *   - several GPUs: ctmr_group_* (one process drives the GPUs of the box: what the Go host calls) or
+ *     ctmr_peer_* (one process per GPU, tables attached through CUDA IPC).  Either way every set
+ *     "serials::<expDate>::<issuer>" has one owner GPU, the map kernels insert straight into the owner's
+ *     table over NVLink, and WasUnknown / counts are globally exact -- the fan-out is invisible above the ABI.
  *   - there is no CPU fallback: without a CUDA device ctmr_create fails with CTMR_E_NO_DEVICE.
  */
 #ifndef CTMR_H
@@ -35,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CTMR_ABI_VERSION 2
+#define CTMR_ABI_VERSION 3
 
 /* ---- batch-level return codes ------------------------------------------------------------ */
 enum {
@@ -46,7 +50,11 @@ enum {
     CTMR_E_TABLE_FULL = -4,       /* known-certificate table exhausted (cf. Redis OOM, rediscache.go:61-63) */
     CTMR_E_TOO_MANY_ISSUERS = -5, /* more distinct issuers than config.max_issuers */
     CTMR_E_NO_DEVICE = -6,        /* no usable CUDA device: the product path has no CPU fallback */
-    CTMR_E_BATCH_TOO_LARGE = -7   /* exceeds config.max_batch_* */
+    CTMR_E_BATCH_TOO_LARGE = -7,  /* exceeds config.max_batch_* */
+    CTMR_E_PAIR_TABLE_FULL = -8,  /* (issuer, expDate) table exhausted: raise config.pair_capacity_log2 */
+    CTMR_E_META_TABLE_FULL = -9,  /* IssuerMetadata string-identity table exhausted: raise config.meta_capacity_log2 */
+    CTMR_E_PEER_TIMEOUT = -10,    /* a rank of the group did not reach a barrier (a peer failed or the calls diverged) */
+    CTMR_E_PEER = -11             /* peer access / CUDA IPC between the GPUs of a group is not available */
 };
 
 /* ---- per-entry status -------------------------------------------------------------------- */
@@ -83,7 +91,7 @@ typedef struct ctmr_config {
     uint32_t issuer_cn_filter_len;   /*   without trimming, HasPrefix on raw CN bytes (ct-fetch.go:57-63)      */
     uint32_t log_expired_entries;    /* config logExpiredEntries (config/config.go:188) */
     uint32_t flags;                  /* CTMR_F_* */
-    uint32_t reserved;
+    uint32_t meta_capacity_log2;     /* IssuerMetadata string-identity table (issuer DN / CRL-DP bytes), log2 slots; 0 = 20, max 26 */
 } ctmr_config;
 
 /* Caller-allocated per-entry outputs, each [n]; any pointer may be NULL to skip that copy-back. */
@@ -227,7 +235,9 @@ typedef struct ctmr_dev_out { /* device pointers, each [n]; NULL = not produced 
 
 /* map half: DER walk + filter + SHA-256 -> status, exp_hour, serial span, fingerprint, key records */
 int ctmr_map_device(ctmr_ctx* ctx, const ctmr_dev_batch* batch, const ctmr_dev_out* out, void* stream);
-/* reduce half over m key records in any order: insert, resolve lowest-index-wins, per-issuer counts */
+/* reduce half over m key records in any order WITHIN the call: insert, resolve lowest-index-wins, per-issuer
+ * counts.  Across calls the ordering contract of the path holds: every index of a later call must be higher than
+ * every index of an earlier call (a lower index arriving later would find itself "first" a second time). */
 int ctmr_reduce_device(ctmr_ctx* ctx, const ctmr_key* keys, uint64_t m, uint8_t* was_unknown /* [m] */,
                        uint8_t* first_issuer_hour /* [m] */, void* stream);
 /* map + reduce on one GPU */
@@ -263,6 +273,56 @@ int ctmr_read_histogram_device(ctmr_ctx* ctx, uint64_t* counts_dst, uint32_t n_s
 int ctmr_reset_device(ctmr_ctx* ctx, void* stream);
 /* fails with CTMR_E_TABLE_FULL / CTMR_E_CUDA if any asynchronous launch since the last check failed */
 int ctmr_check_device(ctmr_ctx* ctx, void* stream);
+
+/* ---- several GPUs, ONE process (what a Go host uses: SURVEY.md §8(b) "fan-out inside the library") ------------ */
+/* The worker pool of StartDatabaseThreads (cmd/ct-fetch/ct-fetch.go:140-145) becomes one call per drained batch:
+ * the group cuts the batch into rounds of n_devices slices by entry index (entry i keeps global index
+ * next_index + i, so the result equals the sequential numThreads=1 run over the batch in its given order), every
+ * GPU maps its slice and inserts each key into the table of the set's owner GPU over NVLink, events separate the
+ * inserts from the read-back, and the outputs land in the caller's arrays in entry order.  cfg->device is ignored;
+ * `devices` may name a device more than once (several shards on one GPU: how the path is tested on a 1-GPU box). */
+typedef struct ctmr_group ctmr_group;
+int ctmr_group_create(const ctmr_config* cfg, const int32_t* devices, uint32_t n_devices, ctmr_group** out);
+void ctmr_group_destroy(ctmr_group* g);
+const char* ctmr_group_last_error(ctmr_group* g);
+uint32_t ctmr_group_size(ctmr_group* g);
+ctmr_ctx* ctmr_group_member(ctmr_group* g, uint32_t rank); /* read-side access to one shard; owned by the group */
+/* same arguments and outputs as ctmr_process_batch; globally exact across the GPUs of the group */
+int ctmr_group_process_batch(ctmr_group* g, const uint8_t* blob, const uint64_t* offsets, uint64_t n, const uint8_t* issuer_blob,
+                             const uint64_t* issuer_offsets, uint32_t n_issuers, const uint32_t* issuer_idx, int64_t now_unix_ns,
+                             ctmr_out* out);
+int ctmr_group_issuer_counts(ctmr_group* g, uint8_t* digests, uint64_t* counts, size_t* n);   /* summed over the shards */
+int ctmr_group_set_cardinality(ctmr_group* g, int64_t exp_hour, const uint8_t issuer_digest[32], uint64_t* count_out);
+int ctmr_group_status_counters(ctmr_group* g, uint64_t out[CTMR_ST__COUNT]);
+int ctmr_group_table_stats(ctmr_group* g, uint64_t* slots_used, uint64_t* capacity);
+int ctmr_group_preload_known(ctmr_group* g, int64_t exp_hour, const uint8_t issuer_digest[32], const uint8_t* serial_blob,
+                             const uint64_t* serial_offsets, uint64_t n);
+int ctmr_group_evict_expired(ctmr_group* g, int64_t now_unix_sec, uint64_t* evicted_out);
+int ctmr_group_reset(ctmr_group* g);
+
+/* ---- several GPUs, one PROCESS PER GPU (torchrun-style launches) ------------------------------ */
+/* Every rank creates its ctx with the same capacities, exports a handle, gathers all handles by whatever means the
+ * launcher offers (torch.distributed all_gather in this repository) and attaches them.  From then on
+ * ctmr_process_device, ctmr_process_batch, ctmr_reset_device and ctmr_peer_* are COLLECTIVE: every rank must make
+ * the same sequence of calls.  Inside them the ranks meet at barriers kept in peer memory (no host round trip, no
+ * NCCL on the data path); the global index of entry j of rank r's round k is first_index + (k * world + r) * E + j,
+ * i.e. the result equals the sequential run over the rounds in rank order (E = entries per rank and round). */
+#define CTMR_PEER_HANDLE_BYTES 128u
+int ctmr_peer_export(ctmr_ctx* ctx, uint8_t handle_out[CTMR_PEER_HANDLE_BYTES]);
+int ctmr_peer_attach(ctmr_ctx* ctx, uint32_t rank, uint32_t world, const uint8_t* handles /* [world][CTMR_PEER_HANDLE_BYTES] */);
+/* barrier over the group on `stream` (device side; returns immediately) */
+int ctmr_peer_barrier_device(ctmr_ctx* ctx, void* stream);
+/* all-reduce(sum) of [per-issuer unique counts || status counters] over peer memory, bracketed by barriers: the
+ * merge of the per-GPU histograms at the end of a chunk.  Device buffers, uint64 [n_slots] and [CTMR_ST__COUNT]. */
+int ctmr_peer_allreduce_histogram_device(ctmr_ctx* ctx, uint64_t* counts_dst, uint32_t n_slots, uint64_t* status_dst, void* stream);
+/* entries per rank and round of the collective ctmr_process_device (it always runs CTMR_PEER_ROUNDS rounds) */
+#define CTMR_PEER_ROUNDS 4u
+
+/* ---- host placement -------------------------------------------------------------------------------- */
+/* Binds the calling thread to the CPUs of the NUMA node `device` hangs off (sysfs), so that pinned buffers it
+ * allocates and first touches afterwards are node-local: with 8 GPUs reading host memory at PCIe rate, remote-node
+ * buffers halve the end-to-end rate.  Returns the node, or -1 when the topology cannot be read (no change made). */
+int ctmr_bind_host_to_device(int32_t device);
 
 /* ---- measurement tooling -------------------------------------------------------------------- */
 /* Register-only SHA-256 microbenchmark: every lane chains `iters` compressions (K_map's own function, no

@@ -35,7 +35,7 @@ def test_python_binding_covers_header(lib):
 
 
 def test_abi_version(lib):
-    assert lib.ctmr_abi_version() == 2  # 2: ctmr_dev_batch.lens, ctmr_frontend.h
+    assert lib.ctmr_abi_version() == 3  # 3: ctmr_group_* / ctmr_peer_* (several GPUs behind the ABI), per-table error codes
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -58,8 +58,7 @@ def test_struct_layouts_match_header(tmp_path):
     assert capi.KEY_DTYPE.itemsize == 64
 
 
-def test_library_is_blackwell_native():
-    """The shipped .so carries sm_100a SASS with the TMA bulk-copy instruction in the map kernel."""
+def _sass_of(kernel_substr):
     import shutil
     import subprocess
     from ct_mapreduce_b200 import capi
@@ -69,7 +68,27 @@ def test_library_is_blackwell_native():
     elf = subprocess.run([cuobjdump, "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
     sass = subprocess.run([cuobjdump, "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
-    assert "UBLKCP" in sass and "SYNCS" in sass
+    out = [blk for blk in sass.split("Function : ")[1:] if kernel_substr in blk.split("\n", 1)[0]]
+    return out
+
+
+def test_shipped_hot_kernel_is_what_design_md_says():
+    """The product build carries sm_100a SASS only, the hot kernel it ships (and only that instantiation of the streaming
+    map) stages certificates with asynchronous global->shared copies and keeps SHA-256's additions off the ALU pipe;
+    the measured-and-rejected variants (TMA bulk loader, v1, dynamic scheduling) are NOT linked in."""
+    blocks = _sass_of("map_stream_kernel")
+    assert len(blocks) == 1, [b.split("\n", 1)[0] for b in blocks]   # one shipped instantiation: <8,128,0,1>
+    hot = blocks[0]
+    assert "LDGSTS" in hot            # per-lane cp.async staging
+    assert "UBLKCP" not in hot        # the TMA bulk loader is an experiment (CTMR_EXPERIMENTS=1), see DESIGN.md
+    assert hot.count("SHF.") > 150 and hot.count("IMAD") > 100   # rotations on ALU, additions on the FMA pipe
+    assert not _sass_of("map_kernel_v1") and not _sass_of("map_dyn_kernel")
+
+
+def test_peer_atomics_are_system_scope():
+    """The table claims of a multi-GPU group are system-scope atomics (performed at the owner's L2 over NVLink)."""
+    blocks = _sass_of("insert_kernel")
+    assert blocks and any(".SYS" in b or ".STRONG.SYS" in b for b in blocks)
 
 
 def test_no_cpu_fallback_without_gpu(lib):
