@@ -306,9 +306,10 @@ def main():
             dist.all_reduce(t)
         return [int(x) for x in t.tolist()]
 
-    def make_db(table_capacity, w, fl):
+    def make_db(table_capacity, w, fl, entries_per_call):
         db = engine.GpuCertDatabase(device=local, table_capacity=table_capacity, issuer_cn_filter=w["filter"],
-                                    log_expired_entries=w["log_expired"], flags=fl, max_issuers=4096)
+                                    log_expired_entries=w["log_expired"], flags=fl, max_issuers=4096,
+                                    max_round_entries=sharded.round_entries(entries_per_call))
         sharded.attach_peers(db)  # N>1: the owners' tables over CUDA IPC; collective calls from here on
         return db
 
@@ -322,7 +323,7 @@ def main():
     cfg = capi.synth_cfg(world * n, seed=SEED, **wl["synth"])
     blob, offsets, issuer_idx, total_bytes = engine.synth_corpus_device(cfg, rank * n, n, dev)
     iblob, ioffs = engine.synth_issuers(cfg)
-    db = make_db(max(1 << 20, 2 * n), wl, flags)
+    db = make_db(max(1 << 20, 2 * n), wl, flags, n)
     dense = db.register_issuers(iblob, ioffs)
     dense_t = torch.from_numpy(dense.astype(np.int32)).to(dev)
     issuer_dense = dense_t[issuer_idx.long()].contiguous()   # dense registry indices (the registry is shared by the group)
@@ -533,7 +534,7 @@ def main():
             nc = min(w2["n"], per_gpu_entries)
             chunks = max(1, -(-per_gpu_entries // nc))
             cfg2 = capi.synth_cfg(chunks * world * nc, seed=SEED + 1, **w2["synth"])
-            db2 = make_db(pow2(int(1.6 * chunks * nc)), w2, fl)
+            db2 = make_db(pow2(int(1.6 * chunks * nc)), w2, fl, nc)
             try:
                 ib2, io2 = engine.synth_issuers(cfg2)
                 d2 = torch.from_numpy(db2.register_issuers(ib2, io2).astype(np.int32)).to(dev)

@@ -40,7 +40,7 @@ EXPORTS = [
     "ctmr_peer_export", "ctmr_peer_attach", "ctmr_peer_barrier_device", "ctmr_peer_allreduce_histogram_device",
     "ctmr_bind_host_to_device",
 ]
-PEER_HANDLE_BYTES = 128
+PEER_HANDLE_BYTES = 256
 PEER_ROUNDS = 4
 E_PAIR_TABLE_FULL, E_META_TABLE_FULL, E_PEER_TIMEOUT, E_PEER = -8, -9, -10, -11
 
@@ -51,6 +51,7 @@ class Config(C.Structure):
         ("max_batch_entries", C.c_uint64), ("max_batch_bytes", C.c_uint64), ("max_issuers", C.c_uint32),
         ("pair_capacity_log2", C.c_uint32), ("issuer_cn_filter", C.c_char_p), ("issuer_cn_filter_len", C.c_uint32),
         ("log_expired_entries", C.c_uint32), ("flags", C.c_uint32), ("meta_capacity_log2", C.c_uint32),
+        ("max_round_entries", C.c_uint64),
     ]
 
 
@@ -181,7 +182,7 @@ def load():
     L.ctmr_group_preload_known.argtypes = [vp, i64, vp, vp, vp, u64]
     L.ctmr_group_evict_expired.argtypes = [vp, i64, C.POINTER(u64)]
     L.ctmr_group_reset.argtypes = [vp]
-    L.ctmr_peer_export.argtypes = [vp, vp]
+    L.ctmr_peer_export.argtypes = [vp, u32, vp]
     L.ctmr_peer_attach.argtypes = [vp, u32, u32, vp]
     L.ctmr_peer_barrier_device.argtypes = [vp, vp]
     L.ctmr_peer_allreduce_histogram_device.argtypes = [vp, vp, u32, vp, vp]

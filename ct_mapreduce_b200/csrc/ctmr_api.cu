@@ -92,7 +92,7 @@ int ensure_scratch(ctmr_ctx* c, uint64_t n) {
 
 namespace ctmr_host {
 void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, MapParams& p, int counter_slot,
-                     uint32_t* fused_slot_of) {
+                     uint32_t* fused_slot_of, int parity) {
     std::memset(&p, 0, sizeof p);
     p.blob = b->blob;
     p.blob_bytes = b->blob_bytes;
@@ -132,9 +132,18 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
     p.status_counts = c->st.status_counts;
     p.work_counter = c->small_dev + 84 + counter_slot;  // one per pipeline stage + one for the device entry points
     p.filter = c->filter;
-    if (fused_slot_of && p.keys) {  // K_insert fused into K_map: straight into the owner's table, local or over NVLink
-        for (uint32_t r = 0; r < kMaxWorld; ++r) p.table[r] = c->st.peer.table[r];
-        p.world = c->st.peer.world;
+    p.route.world = 1;
+    if (fused_slot_of && p.keys) {  // K_insert fused into K_map: own keys into the own table, the others to their owners' inboxes
+        p.table = c->st.table;
+        const uint32_t W = c->px.world;
+        if (W > 1) {
+            for (uint32_t r = 0; r < W; ++r) p.route.inbox[r] = c->px.inbox[r] + ((uint64_t)parity * W + c->px.rank) * c->px.X;
+            p.route.cursor = c->cursors + (size_t)parity * kMaxWorld;
+            p.route.rev = c->rev + (uint64_t)parity * W * c->px.X;
+            p.route.X = c->px.X;
+            p.route.world = W;
+            p.route.rank = c->px.rank;
+        }
         p.table_mask = c->st.table_mask;
         p.error_flag = c->st.error_flag;
         p.slot_of = fused_slot_of;
@@ -167,6 +176,73 @@ void attach_views(ctmr_ctx* c, uint8_t* const* bases, uint32_t world, uint32_t r
     c->reg.counter = reinterpret_cast<unsigned long long*>(bases[0] + l.reg_counter);
     c->reg.by_index = bases[0] + l.reg_digests;
     c->reg.max_issuers = c->st.max_issuers;
+}
+
+size_t exchange_bytes(uint32_t world, uint64_t X) {
+    return 4096 + (size_t)kParities * world * X * (sizeof(ctmr_key) + 2);
+}
+
+// layout of a rank's exchange area: [counts: kParities x world u64, padded to 4 KiB][inbox][out_wu][out_first]
+void attach_exchange(ctmr_ctx* c, uint8_t* const* bases, uint32_t world, uint32_t rank) {
+    c->px = PeerExchange{};
+    const uint64_t per = (uint64_t)kParities * world * c->X;
+    for (uint32_t r = 0; r < world; ++r) {
+        c->px.counts[r] = reinterpret_cast<unsigned long long*>(bases[r]);
+        c->px.inbox[r] = reinterpret_cast<ctmr_key*>(bases[r] + 4096);
+        c->px.out_wu[r] = bases[r] + 4096 + per * sizeof(ctmr_key);
+        c->px.out_first[r] = c->px.out_wu[r] + per;
+    }
+    c->px.X = c->X;
+    c->px.world = world;
+    c->px.rank = rank;
+}
+
+int alloc_exchange(ctmr_ctx* c, uint32_t world) {
+    if (c->xchg || world <= 1) return CTMR_OK;
+    c->X = c->cfg_round_entries ? c->cfg_round_entries : c->stage_entries;
+    if (c->X < c->stage_entries) c->X = c->stage_entries;  // the host pipeline maps stage_entries per round
+    const size_t per = (size_t)kParities * world * c->X;
+    CU(c, cudaMalloc(&c->xchg, exchange_bytes(world, c->X)));
+    CU(c, cudaMemsetAsync(c->xchg, 0, 4096, c->stream));
+    CU(c, cudaMalloc(&c->cursors, (size_t)kParities * kMaxWorld * sizeof(unsigned long long)));
+    CU(c, cudaMemsetAsync(c->cursors, 0, (size_t)kParities * kMaxWorld * sizeof(unsigned long long), c->stream));
+    CU(c, cudaMalloc(&c->rev, per * sizeof(uint32_t)));
+    CU(c, cudaMalloc(&c->in_slot, per * sizeof(uint32_t)));
+    CU(c, cudaMalloc(&c->in_pair, per * sizeof(uint32_t)));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CTMR_OK;
+}
+
+int round_begin(ctmr_ctx* c, int parity, cudaStream_t s) {
+    if (c->px.world <= 1) return CTMR_OK;
+    CU(c, cudaMemsetAsync(c->cursors + (size_t)parity * kMaxWorld, 0, kMaxWorld * sizeof(unsigned long long), s));
+    return CTMR_OK;
+}
+int round_publish(ctmr_ctx* c, int parity, cudaStream_t s) {
+    if (c->px.world <= 1) return CTMR_OK;
+    CU(c, launch_publish_counts(c->px, (uint32_t)parity, c->cursors + (size_t)parity * kMaxWorld, s));
+    return CTMR_OK;
+}
+int round_owner_insert(ctmr_ctx* c, int parity, uint64_t maxr, cudaStream_t s) {
+    if (c->px.world <= 1) return CTMR_OK;
+    CU(c, launch_inbox_insert(c->st, c->px, (uint32_t)parity, maxr, c->in_slot, s));
+    return CTMR_OK;
+}
+int round_owner_resolve(ctmr_ctx* c, int parity, uint64_t maxr, cudaStream_t s) {
+    if (c->px.world <= 1) return CTMR_OK;
+    CU(c, launch_inbox_resolve(c->st, c->px, (uint32_t)parity, maxr, c->in_slot, c->in_pair, s));
+    return CTMR_OK;
+}
+int round_owner_pairs(ctmr_ctx* c, int parity, uint64_t maxr, cudaStream_t s) {
+    if (c->px.world <= 1) return CTMR_OK;
+    CU(c, launch_inbox_pairs(c->st, c->px, (uint32_t)parity, maxr, c->in_pair, s));
+    return CTMR_OK;
+}
+int round_pull(ctmr_ctx* c, int parity, uint64_t maxr, uint8_t* was_unknown, uint8_t* first, cudaStream_t s) {
+    if (c->px.world <= 1) return CTMR_OK;
+    CU(c, launch_pull_bits(c->px, (uint32_t)parity, c->cursors + (size_t)parity * kMaxWorld,
+                           c->rev + (uint64_t)parity * c->px.world * c->px.X, maxr, was_unknown, first, s));
+    return CTMR_OK;
 }
 
 int peer_barrier(ctmr_ctx* c, uint32_t channel, cudaStream_t s) {
@@ -441,6 +517,8 @@ int ctmr_create(const ctmr_config* cfg, ctmr_ctx** out) {
                                               : kStageEntries;
     const uint64_t want_bytes = cfg->max_batch_bytes ? cfg->max_batch_bytes : c->stage_entries * 2048ull;
     c->stage_bytes = want_bytes < kStageBytes ? want_bytes : kStageBytes;
+    c->cfg_round_entries = cfg->max_round_entries;
+    c->px.world = 1;
     if (const char* ev = getenv("CTMR_BUCKET_BY_LENGTH")) c->bucket_by_length = atoi(ev) != 0;
     if (const char* ev = getenv("CTMR_FUSE_INSERT")) c->fuse_insert = atoi(ev) != 0;
     if (const char* ev = getenv("CTMR_MAP_VARIANT")) if (atoi(ev) != 2) c->fuse_insert = false;  // only the streaming kernel fuses
@@ -455,8 +533,13 @@ void ctmr_destroy(ctmr_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     stages_destroy(c);
-    for (uint32_t r = 0; r < kMaxWorld; ++r)
+    for (uint32_t r = 0; r < kMaxWorld; ++r) {
         if (c->ipc_base[r]) cudaIpcCloseMemHandle(c->ipc_base[r]);
+        if (c->ipc_xchg[r]) cudaIpcCloseMemHandle(c->ipc_xchg[r]);
+    }
+    cudaFree(c->xchg); cudaFree(c->cursors); cudaFree(c->rev); cudaFree(c->in_slot); cudaFree(c->in_pair);
+    for (cudaEvent_t e : c->ev_pulled)
+        if (e) cudaEventDestroy(e);
     cudaFree(c->shared); cudaFree(c->small_dev);
     cudaFree(c->issuer_map_dev); cudaFree(c->keys_scratch); cudaFree(c->slot_scratch); cudaFree(c->pair_scratch);
     cudaFree(c->bits_scratch); cudaFree(c->meta_scratch); cudaFree(c->order_scratch); cudaFree(c->len_hist);
@@ -705,6 +788,7 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
             CU(c, cudaEventCreate(&c->ev_red1[k]));
             CU(c, cudaMalloc(&c->len_hist_sub[k], 256 * sizeof(unsigned int)));
         }
+        for (cudaEvent_t& e : c->ev_pulled) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     const bool want_meta = o->first_issuer_dn || o->first_crldp;
     if (want_meta && !(o->issuer_name_off && o->issuer_name_len && o->crldp_off && o->crldp_len))
@@ -721,6 +805,8 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
         return fail(c, CTMR_E_INVALID, "members of an in-process group are driven through ctmr_group_process_batch");
     const int nsub = coll ? (int)CTMR_PEER_ROUNDS : (b->n >= (1u << 21) ? 4 : (b->n >= (1u << 18) ? 2 : 1));
     const uint64_t per_round = (b->n + nsub - 1) / nsub;
+    if (coll && per_round > c->px.X)
+        return fail(c, CTMR_E_BATCH_TOO_LARGE, "entries per round exceed the key-exchange regions: raise config.max_round_entries to ceil(n / CTMR_PEER_ROUNDS)");
     ctmr_key* keys = o->keys ? o->keys : c->keys_scratch;
     uint8_t* wu = o->was_unknown ? o->was_unknown : c->bits_scratch;
     uint8_t* fi = o->first_issuer_hour ? o->first_issuer_hour : c->bits_scratch + b->n;
@@ -754,30 +840,47 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
         so.issuer_name_len = o->issuer_name_len ? o->issuer_name_len + lo : nullptr;
         so.crldp_off = o->crldp_off ? o->crldp_off + lo : nullptr;
         so.crldp_len = o->crldp_len ? o->crldp_len + lo : nullptr;
+        const int parity = k & 1;
+        const bool fused = c->fuse_insert || world > 1;   // a group always fuses: the routing happens in K_map's epilogue
         MapParams p;
-        fill_map_params(c, &sb, &so, p, 3, c->fuse_insert ? c->slot_scratch + lo : nullptr);
+        fill_map_params(c, &sb, &so, p, 3, fused ? c->slot_scratch + lo : nullptr, parity);
+        if (world > 1 && k >= 2) CU(c, cudaStreamWaitEvent(c->stream_a, c->ev_pulled[parity], 0));  // the parity's regions are free again
         CU(c, cudaEventRecord(c->ev_map0[k], c->stream_a));
+        rc = round_begin(c, parity, c->stream_a);
+        if (rc) return rc;
         if (c->bucket_by_length && cnt > 64 && p.sha256) {
             CU(c, launch_len_order(sb.offsets, sb.lens, cnt, sb.blob_bytes, c->len_hist_sub[k], c->order_scratch + lo, c->stream_a));
             p.order = c->order_scratch + lo;
         }
         CU(c, launch_map(p, c->sm_count, c->stream_a));
         CU(c, cudaEventRecord(c->ev_map1[k], c->stream_a));
-        CU(c, cudaStreamWaitEvent(c->stream_b, c->ev_map1[k], 0));
+        rc = round_publish(c, parity, c->stream_a);  // region sizes to the owners (outside K_map's timed bracket)
+        if (rc) return rc;
+        CU(c, cudaEventRecord(c->ev_join_a, c->stream_a));   // ordering token: K_map + the published sizes
+        CU(c, cudaStreamWaitEvent(c->stream_b, c->ev_join_a, 0));
         cudaStream_t sbm = c->stream_b;
-        if (!c->fuse_insert) CU(c, launch_insert(c->st, keys + lo, cnt, c->slot_scratch + lo, sbm));
-        rc = peer_barrier(c, CH_DEV_MAP, sbm);  // every rank's inserts of rounds <= k are in the owners' tables
+        if (!fused) CU(c, launch_insert(c->st, keys + lo, cnt, c->slot_scratch + lo, sbm));
+        rc = peer_barrier(c, CH_DEV_MAP, sbm);  // every rank's appends of rounds <= k have landed in the owners' inboxes
+        if (rc) return rc;
+        rc = round_owner_insert(c, parity, per_round, sbm);
         if (rc) return rc;
         CU(c, launch_resolve(c->st, keys + lo, cnt, c->slot_scratch + lo, c->pair_scratch + lo, wu + lo, sbm));
-        if (want_meta)  // IssuerMetadata string identities of this round's new certificates
-            CU(c, launch_meta_insert(c->st, sb.blob, sb.offsets, keys + lo, cnt, wu + lo, so.issuer_name_off, so.issuer_name_len,
-                                     so.crldp_off, so.crldp_len, c->meta_scratch + 2 * lo, sbm));
-        rc = peer_barrier(c, CH_DEV_RESOLVE, sbm);  // ... and their first-seen candidates in the owners' pair tables
+        rc = round_owner_resolve(c, parity, per_round, sbm);
         if (rc) return rc;
         CU(c, launch_resolve_pairs(c->st, keys + lo, cnt, c->pair_scratch + lo, wu + lo, fi + lo, sbm));
-        if (want_meta)
-            CU(c, launch_meta_resolve(c->st, keys + lo, cnt, c->meta_scratch + 2 * lo, o->first_issuer_dn ? o->first_issuer_dn + lo : nullptr,
-                                      o->first_crldp ? o->first_crldp + lo : nullptr, sbm));
+        rc = round_owner_pairs(c, parity, per_round, sbm);
+        if (rc) return rc;
+        rc = peer_barrier(c, CH_DEV_RESOLVE, sbm);  // every owner has the result bits of this round's records ready
+        if (rc) return rc;
+        rc = round_pull(c, parity, per_round, wu + lo, fi + lo, sbm);
+        if (rc) return rc;
+        if (world > 1) CU(c, cudaEventRecord(c->ev_pulled[parity], sbm));
+        if (want_meta) {
+            if (world > 1) return fail(c, CTMR_E_INVALID, "first_issuer_dn / first_crldp of a group come from the host-buffer call");
+            CU(c, launch_meta(c->st, sb.blob, sb.offsets, keys + lo, cnt, wu + lo, so.issuer_name_off, so.issuer_name_len, so.crldp_off,
+                              so.crldp_len, c->meta_scratch + 2 * lo, o->first_issuer_dn ? o->first_issuer_dn + lo : nullptr,
+                              o->first_crldp ? o->first_crldp + lo : nullptr, sbm));
+        }
         CU(c, cudaEventRecord(c->ev_red1[k], c->stream_b));
     }
     c->last_sub = nsub;
@@ -897,6 +1000,11 @@ int preload_impl(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], const 
     int rc = lookup_digest(c, digest, true, &issuer, &found);  // the issuer may be unknown so far (state written by an earlier process)
     if (rc) return rc;
     if (!n) return CTMR_OK;
+    if (c->st.peer.world > 1) {
+        const uint32_t owner = key_owner((int32_t)exp_hour, issuer, c->st.peer.world);
+        if (owner != c->st.peer.rank)
+            return fail(c, CTMR_E_INVALID, "this set is owned by rank " + std::to_string(owner) + " of the group: preload it there");
+    }
     std::vector<ctmr_key> keys(n);
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t len = serial_offsets[i + 1] - serial_offsets[i];

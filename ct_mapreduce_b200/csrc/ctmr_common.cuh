@@ -96,10 +96,10 @@ __device__ __forceinline__ unsigned long long tab_load_acquire(const unsigned lo
 // 16 bytes of a slot that another GPU may have written: never from a stale L1 line
 __device__ __forceinline__ uint4 ld_cv_u4(const uint4* p) { return __ldcv(p); }
 
-// Find-or-insert of a 48-byte key body in the OWNER's table (possibly another GPU's, over NVLink); lowest global
-// index wins through an atomic max on ~index.  One round trip claims an empty slot (optimistic CAS: the tag read
-// is the CAS's return value), the key bytes and the ready tag follow as posted writes (release store).  Returns
-// the slot, or 0xFFFFFFFF when the table is full (error flag set).  Shared by K_insert and by K_map's fused insert.
+// Find-or-insert of a 48-byte key body; lowest global index wins through an atomic max on ~index.  An empty slot is
+// claimed by an optimistic CAS (the tag read is the CAS's return value), the key bytes are published by a release
+// store of the ready tag.  Returns the slot, or 0xFFFFFFFF when the table is full (error flag set).  Shared by
+// K_insert and by K_map's fused insert; SYS = system scope (only the string-identity table is touched across GPUs).
 template <bool SYS>
 __device__ __forceinline__ uint32_t known_insert(KnownSlot* __restrict__ table, uint64_t table_mask, int* error_flag,
                                                  const uint32_t (&body)[12], unsigned long long inv_idx) {
@@ -137,13 +137,6 @@ __device__ __forceinline__ uint32_t known_insert(KnownSlot* __restrict__ table, 
             return 0xFFFFFFFFu;
         }
     }
-}
-
-// owner dispatch: the key (exp_hour, issuer) picks the GPU whose table holds the set
-__device__ __forceinline__ uint32_t known_insert_owner(KnownSlot* const* tables, uint32_t world, uint64_t table_mask, int* error_flag,
-                                                       const uint32_t (&body)[12], unsigned long long inv_idx) {
-    if (world <= 1u) return known_insert<false>(tables[0], table_mask, error_flag, body, inv_idx);
-    return known_insert<true>(tables[key_owner((int32_t)body[0], body[1], world)], table_mask, error_flag, body, inv_idx);
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {

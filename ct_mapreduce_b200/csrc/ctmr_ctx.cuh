@@ -13,6 +13,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "ctmr_device.cuh"
 #include "ctmr_kernels.cuh"
 
 using namespace ctmr;
@@ -38,7 +39,8 @@ struct PemStage {
 struct Stage {
     cudaStream_t stream = nullptr;
     cudaEvent_t mapped = nullptr;   // recorded after this stage's K_map (its inserts have reached the owners' tables)
-    cudaEvent_t reduced = nullptr;  // recorded after this stage's resolve (+ string-identity insert) kernels
+    cudaEvent_t reduced = nullptr;  // recorded after this stage's owner passes (resolve + pairs of own entries and inbox records)
+    cudaEvent_t meta_done = nullptr;  // recorded after this stage's string-identity insert
     uint8_t* blob = nullptr;
     uint64_t* offsets = nullptr;
     uint32_t* issuer_idx = nullptr;
@@ -127,7 +129,8 @@ enum : uint32_t {
     CH_STAGE_MAP = 0,      // + stage index (3): after K_map of a host-pipeline round
     CH_STAGE_RESOLVE = 3,  // + stage index (3): after resolve of a host-pipeline round
     CH_DEV_MAP = 6, CH_DEV_RESOLVE = 7,  // ctmr_process_device
-    CH_USER = 8, CH_HIST_A = 9, CH_HIST_B = 10, CH_RESET_A = 11, CH_RESET_B = 12, CH_MAILBOX = 13
+    CH_USER = 8, CH_HIST_A = 9, CH_HIST_B = 10, CH_RESET_A = 11, CH_RESET_B = 12, CH_MAILBOX = 13,
+    CH_STAGE_META = 16                   // + stage index (3): after the string-identity insert of a host-pipeline round
 };
 
 struct ctmr_ctx {
@@ -148,6 +151,15 @@ struct ctmr_ctx {
     IssuerRegistry reg{};                  // lives in rank 0's region
     int peer_mode = PEER_NONE;
     void* ipc_base[kMaxWorld] = {};        // mappings opened with cudaIpcOpenMemHandle (closed on destroy)
+    void* ipc_xchg[kMaxWorld] = {};
+    // key exchange of a group: peer-visible area (inboxes, result bits, region sizes) + private bookkeeping
+    uint8_t* xchg = nullptr;
+    uint64_t X = 0, cfg_round_entries = 0;
+    PeerExchange px{};
+    unsigned long long* cursors = nullptr;  // [kParities][kMaxWorld] records appended per owner (local)
+    uint32_t* rev = nullptr;                // [kParities][world][X] inbox position -> entry
+    uint32_t *in_slot = nullptr, *in_pair = nullptr;  // [kParities][world][X] owner-side scratch of the inbox records
+    cudaEvent_t ev_pulled[2] = {};          // ctmr_process_device: round k's bits pulled (its exchange parity may be reused)
     unsigned long long epoch[kPeerChannels] = {};
     struct ctmr_group* group = nullptr;    // set when the ctx is a member of an in-process group
     // issuer memo on the host (the registry itself is on the device): DER -> index, digest -> index, index -> digest
@@ -201,7 +213,18 @@ int fail(ctmr_ctx* ctx, int code, const std::string& msg);
 
 uint64_t pow2_at_least(uint64_t v);
 void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, MapParams& p, int counter_slot = 3,
-                     uint32_t* fused_slot_of = nullptr);
+                     uint32_t* fused_slot_of = nullptr, int parity = 0);
+// key exchange: allocation for a group of `world` ranks, views of every rank's area
+size_t exchange_bytes(uint32_t world, uint64_t X);
+int alloc_exchange(ctmr_ctx* c, uint32_t world);
+void attach_exchange(ctmr_ctx* c, uint8_t* const* bases, uint32_t world, uint32_t rank);
+// one round of the exchange on stream s (no-ops on a single GPU)
+int round_begin(ctmr_ctx* c, int parity, cudaStream_t s);                       // before K_map: cursors of this parity to 0
+int round_publish(ctmr_ctx* c, int parity, cudaStream_t s);                     // after K_map: region sizes to the owners
+int round_owner_insert(ctmr_ctx* c, int parity, uint64_t max_per_region, cudaStream_t s);   // owner: inbox records into the table
+int round_owner_resolve(ctmr_ctx* c, int parity, uint64_t max_per_region, cudaStream_t s);  // ... their was_unknown, counts, pair slots
+int round_owner_pairs(ctmr_ctx* c, int parity, uint64_t max_per_region, cudaStream_t s);    // ... their first_issuer_hour
+int round_pull(ctmr_ctx* c, int parity, uint64_t max_per_region, uint8_t* was_unknown, uint8_t* first, cudaStream_t s);
 // views of the shared regions `bases[0..world)` (this rank's own among them) -> st.peer, pf, reg
 void attach_views(ctmr_ctx* c, uint8_t* const* bases, uint32_t world, uint32_t rank);
 int peer_barrier(ctmr_ctx* c, uint32_t channel, cudaStream_t s);   // PEER_IPC only; no-op otherwise

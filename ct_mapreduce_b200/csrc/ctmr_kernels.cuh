@@ -44,11 +44,34 @@ struct __align__(16) MetaSlot {      // IssuerMetadata string sets: identity = t
 };
 
 // Multi-GPU: every set "serials::<expDate>::<issuer>" has ONE owner GPU
-// (key_owner(exp_hour, issuer, world)), which holds its serials, its (issuer, hour) slot and -- by the hash of
-// the string -- the IssuerMetadata identities.  The owners' tables are mapped into every rank (peer access in one
-// process, CUDA IPC across processes) and the kernels address them directly over NVLink: slot claims are
-// system-scope atomicCAS, lowest-index-wins is a system-scope atomicMax, results are read back after a barrier.
+// (key_owner(exp_hour, issuer, world)), which holds its serials and its (issuer, hour) slot, and does every table
+// operation on them with device-scope atomics in its own HBM.  What crosses NVLink is BULK traffic only (measured:
+// fine-grained remote atomics run at ~0.4 G ops/s per GPU and made K_map 4x slower, profiles/r2_peer_atomics_2gpu.json):
+// K_map appends the 64-byte key record of an entry owned elsewhere to a per-source region of the owner's INBOX
+// (coalesced posted writes, cursors in local memory), the owner inserts / resolves its inbox after a barrier, and the
+// source pulls the result bits back as contiguous arrays.  The peers' memory is mapped into every rank (peer access
+// in one process, CUDA IPC across processes).
 constexpr uint32_t kMaxWorld = 8;
+constexpr uint32_t kParities = 3;   // exchange buffers in flight: the host pipeline's three stages / two rounds of the device path
+
+// exchange areas of every rank (peer visible).  Region of (parity p, source s) = element offset (p * world + s) * X.
+struct PeerExchange {
+    ctmr_key* inbox[kMaxWorld];             // [kParities][world][X] key records appended by the sources
+    uint8_t* out_wu[kMaxWorld];             // [kParities][world][X] was_unknown of the inbox records, same positions
+    uint8_t* out_first[kMaxWorld];          // [kParities][world][X] first_issuer_hour
+    unsigned long long* counts[kMaxWorld];  // [kParities][world] records per source region, published by the sources
+    uint64_t X;                             // capacity of a region = the most entries one rank maps per round
+    uint32_t world, rank;
+};
+
+// what K_map needs to route the keys of one round
+struct RouteOut {
+    ctmr_key* inbox[kMaxWorld];   // owner o's region for THIS source and this round's parity
+    unsigned long long* cursor;   // local [world]: records appended per owner so far
+    uint32_t* rev;                // local [world][X]: inbox position -> entry of this round (for the pull)
+    uint64_t X;
+    uint32_t world, rank;
+};
 
 struct PeerTables {
     KnownSlot* table[kMaxWorld];
@@ -86,7 +109,7 @@ struct PeerFlags {
     uint32_t world, rank;
     unsigned long long timeout_ns;                 // a barrier wait longer than this raises CTMR_E_PEER_TIMEOUT
 };
-constexpr uint32_t kPeerChannels = 16;
+constexpr uint32_t kPeerChannels = 20;
 
 struct DeviceState {
     KnownSlot* table;          // this rank's shard (== peer.table[peer.rank])
@@ -131,10 +154,10 @@ struct MapParams {
     unsigned long long* status_counts;
     unsigned long long* work_counter;  // [1] scratch of the dynamically scheduled map kernel
     const uint32_t* order;             // [n] length-bucketed processing order (NULL = entry order)
-    // fused K_insert (slot_of != NULL): the owners' known-certificate tables and where each entry's slot goes
-    KnownSlot* table[kMaxWorld];
-    uint32_t world;
-    uint32_t pad_world;
+    // fused K_insert (slot_of != NULL): keys this rank owns go straight into its table (slot -> slot_of), keys owned
+    // elsewhere are appended to the owner's inbox (slot_of = 0xFFFFFFFF)
+    KnownSlot* table;
+    RouteOut route;
     uint64_t table_mask;
     int* error_flag;
     uint32_t* slot_of;
@@ -152,6 +175,17 @@ cudaError_t launch_resolve(const DeviceState& st, const ctmr_key* keys, uint64_t
                            uint32_t* pair_slot, uint8_t* was_unknown, cudaStream_t s);
 cudaError_t launch_resolve_pairs(const DeviceState& st, const ctmr_key* keys, uint64_t m, const uint32_t* pair_slot,
                                  const uint8_t* was_unknown, uint8_t* first_issuer_hour, cudaStream_t s);
+// owner side of the exchange: the same three passes over the inbox regions of one parity (record counts on the device)
+cudaError_t launch_inbox_insert(const DeviceState& st, const PeerExchange& px, uint32_t parity, uint64_t max_per_region, uint32_t* in_slot,
+                                cudaStream_t s);
+cudaError_t launch_inbox_resolve(const DeviceState& st, const PeerExchange& px, uint32_t parity, uint64_t max_per_region,
+                                 const uint32_t* in_slot, uint32_t* in_pair, cudaStream_t s);
+cudaError_t launch_inbox_pairs(const DeviceState& st, const PeerExchange& px, uint32_t parity, uint64_t max_per_region,
+                               const uint32_t* in_pair, cudaStream_t s);
+// source side: publish the region sizes to the owners (before the barrier), pull the result bits (after the second one)
+cudaError_t launch_publish_counts(const PeerExchange& px, uint32_t parity, const unsigned long long* cursor, cudaStream_t s);
+cudaError_t launch_pull_bits(const PeerExchange& px, uint32_t parity, const unsigned long long* cursor, const uint32_t* rev,
+                             uint64_t max_per_region, uint8_t* was_unknown, uint8_t* first_issuer_hour, cudaStream_t s);
 cudaError_t launch_meta(const DeviceState& st, const uint8_t* blob, const uint64_t* offsets, const ctmr_key* keys, uint64_t m,
                         const uint8_t* was_unknown, const uint32_t* name_off, const uint32_t* name_len, const uint32_t* crl_off,
                         const uint32_t* crl_len, uint32_t* meta_slots /* [2*m] scratch */, uint8_t* first_dn, uint8_t* first_crl,

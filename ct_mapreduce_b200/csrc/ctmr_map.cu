@@ -21,6 +21,29 @@
 
 namespace ctmr {
 
+// Appends the finished 64-byte key record `kr` (local memory) of an entry owned by another GPU to that owner's inbox:
+// lanes of the warp that route to the same owner take consecutive positions from ONE atomic on a cursor in LOCAL
+// memory, so the records of a (warp, owner) group form one contiguous run of posted NVLink writes.  rev[] remembers
+// which entry sits at which inbox position (the result bits come back by position).  Called by every lane that is
+// inside the caller's active region, remote or not.
+__device__ __forceinline__ void route_append(const RouteOut& r, bool remote, uint32_t owner, const uint4* kr, uint32_t entry) {
+    if (r.world <= 1u) return;
+    const uint32_t rmask = __ballot_sync(__activemask(), remote);
+    if (!remote) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t peers = __match_any_sync(rmask, owner);
+    const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(r.cursor + owner, (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint64_t i = base + __popc(peers & ((1u << lane) - 1u));
+    if (i >= r.X) return;  // cannot happen: the host checks entries-per-round <= X
+    const uint4 q0 = kr[0], q1 = kr[1], q2 = kr[2], q3 = kr[3];
+    uint4* dst = reinterpret_cast<uint4*>(r.inbox[owner] + i);
+    dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
+    r.rev[(uint64_t)owner * r.X + i] = entry;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K_map_light: the map WITHOUT the whole-certificate fingerprint (CTMR_F_NO_FINGERPRINT, i.e. the
 // reference's own semantics: it never hashes the leaf).  With no SHA-256 there is
@@ -113,7 +136,12 @@ __global__ void __launch_bounds__(256, 4) map_light_kernel(const __grid_constant
             kr[1] = make_uint4(body[2], body[3], body[4], body[5]);
             kr[2] = make_uint4(body[6], body[7], body[8], body[9]);
             kr[3] = make_uint4(body[10], body[11], valid ? 1u : 0u, 0u);
-            if (p.slot_of) p.slot_of[e] = valid ? known_insert_owner(p.table, p.world, p.table_mask, p.error_flag, body, ~gi) : 0xFFFFFFFFu;
+            if (p.slot_of) {
+                const uint32_t owner = (valid && p.route.world > 1u) ? key_owner((int32_t)body[0], body[1], p.route.world) : p.route.rank;
+                const bool remote = valid && owner != p.route.rank;
+                p.slot_of[e] = (valid && !remote) ? known_insert<false>(p.table, p.table_mask, p.error_flag, body, ~gi) : 0xFFFFFFFFu;
+                route_append(p.route, remote, owner, kr, (uint32_t)e);
+            }
         }
     }
     if (p.status_counts) {
@@ -322,14 +350,17 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
                     // fused K_insert (single-GPU path): the probe's random HBM accesses hide under the
                     // INT-bound SHA work of the other warps instead of costing a latency-bound pass
                     uint32_t slot = 0xFFFFFFFFu;
-                    if (valid) {
+                    const uint32_t owner = (valid && p.route.world > 1u) ? key_owner((int32_t)exp_hour, issuer, p.route.world) : p.route.rank;
+                    const bool remote = valid && owner != p.route.rank;
+                    if (valid && !remote) {
                         const uint4 k1 = kr[1], k2 = kr[2];  // the serial words the walker stored (L2-resident)
                         const uint2 k3 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(kr) + 12);
                         const uint32_t body[12] = {(uint32_t)(int32_t)exp_hour, issuer, k1.x, k1.y, k1.z, k1.w,
                                                    k2.x, k2.y, k2.z, k2.w, k3.x, k3.y};
-                        slot = known_insert_owner(p.table, p.world, p.table_mask, p.error_flag, body, ~gi);
+                        slot = known_insert<false>(p.table, p.table_mask, p.error_flag, body, ~gi);
                     }
                     p.slot_of[e] = slot;
+                    route_append(p.route, remote, owner, kr, (uint32_t)e);  // keys owned elsewhere: into the owner's inbox over NVLink
                 }
             }
             if (want_sha) {

@@ -5,13 +5,15 @@
 // most `stage_entries` entries and runs, on the stream of the round's stage (three stages rotate, so H2D, kernels
 // and D2H of consecutive rounds overlap):
 //
-//     H2D slice -> K_map (DER walk + filter + SHA-256, the table insert fused in: each key goes straight into the
-//                  table of its set's OWNER GPU, over NVLink when that is a peer)
-//     -- sync 1: every member's inserts of this round are done --
-//     K_resolve (was_unknown = "mine is the lowest index in the owner's slot"; per-issuer counts at home;
-//                (issuer, hour) first-seen + cardinality at the owner) [+ string-identity insert]
-//     -- sync 2: every member's resolve of this round is done --
-//     K_pairs (first_issuer_hour) [+ string-identity resolve] -> D2H of the requested outputs [-> PEM]
+//     H2D slice -> K_map (DER walk + filter + SHA-256 + key routing: a key of a set this GPU owns goes straight into
+//                  its table, any other key is appended as a 64-byte record to the OWNER's inbox over NVLink)
+//     -- sync 1: every member's appends of this round have landed --
+//     owner passes: insert of the inbox records; K_resolve (was_unknown = "mine is the lowest index of the slot",
+//                  per-issuer counts, (issuer, hour) first-seen + cardinality) and K_pairs (first_issuer_hour) over
+//                  the own entries AND the inbox records, whose bits go to the owner's outbox
+//     -- sync 2: every owner's bits of this round are ready --
+//     pull of the bits of the entries routed away (contiguous peer reads) [-> string identities: insert, sync 3,
+//                  read-back] -> D2H of the requested outputs [-> PEM]
 //
 // sync = nothing on one GPU; CUDA events recorded on every member's stream and waited for by every member's stream
 // in a one-process group; a barrier kernel spinning on flags in peer memory between processes.  Rounds are ordered
@@ -34,6 +36,7 @@ int ensure_stages(ctmr_ctx* c) {
         CU(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(c, cudaEventCreateWithFlags(&s.mapped, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&s.reduced, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&s.meta_done, cudaEventDisableTiming));
         CU(c, cudaMalloc(&s.blob, c->stage_bytes + 64));
         CU(c, cudaMalloc(&s.offsets, (E + 1) * sizeof(uint64_t)));
         CU(c, cudaMalloc(&s.issuer_idx, E * sizeof(uint32_t)));
@@ -66,6 +69,7 @@ void stages_destroy(ctmr_ctx* c) {
         pem_free(s.pem);
         if (s.mapped) cudaEventDestroy(s.mapped);
         if (s.reduced) cudaEventDestroy(s.reduced);
+        if (s.meta_done) cudaEventDestroy(s.meta_done);
         if (s.stream) cudaStreamDestroy(s.stream);
         s = Stage{};
     }
@@ -181,6 +185,9 @@ int agree_rounds(ctmr_ctx* c, uint64_t mine, uint64_t* agreed) {
 int issue_map(ctmr_ctx* c, Stage& s, int sidx, const BatchArgs& a, const Slice& sl, const uint32_t* map_dev, bool want_meta) {
     CU(c, cudaSetDevice(c->device));
     const uint64_t cnt = sl.hi - sl.lo;
+    const bool fused = c->fuse_insert || c->px.world > 1;  // a group always fuses: the routing is K_map's epilogue
+    int rc = round_begin(c, sidx, s.stream);  // exchange parity = stage
+    if (rc) return rc;
     if (cnt) {
         const uint64_t bytes = a.offsets[sl.hi] - a.offsets[sl.lo];
         if (bytes) CU(c, cudaMemcpyAsync(s.blob, a.blob + a.offsets[sl.lo], bytes, cudaMemcpyHostToDevice, s.stream));
@@ -211,28 +218,46 @@ int issue_map(ctmr_ctx* c, Stage& s, int sidx, const BatchArgs& a, const Slice& 
             dout.crldp_len = s.spans + 3 * E;
         }
         MapParams p;
-        fill_map_params(c, &db, &dout, p, sidx, c->fuse_insert ? s.slot_of : nullptr);
+        fill_map_params(c, &db, &dout, p, sidx, fused ? s.slot_of : nullptr, sidx);
         if (c->bucket_by_length && cnt > 64 && p.sha256) {
             CU(c, launch_len_order(s.offsets, nullptr, cnt, db.blob_bytes, s.len_hist, s.order, s.stream));
             p.order = s.order;
         }
         CU(c, launch_map(p, c->sm_count, s.stream));
         // inserts commute (atomic max on ~index); only RESOLVE must see every earlier entry inserted
-        if (!c->fuse_insert) CU(c, launch_insert(c->st, s.keys, cnt, s.slot_of, s.stream));
+        if (!fused) CU(c, launch_insert(c->st, s.keys, cnt, s.slot_of, s.stream));
     }
+    rc = round_publish(c, sidx, s.stream);  // how many records this rank left in each owner's inbox
+    if (rc) return rc;
     CU(c, cudaEventRecord(s.mapped, s.stream));
     return CTMR_OK;
 }
 
-int issue_resolve(ctmr_ctx* c, Stage& s, const BatchArgs& a, const Slice& sl, bool want_meta) {
+// the owner's work of a round: the records other ranks left in its inbox and its own entries' keys
+int issue_owner_insert(ctmr_ctx* c, Stage& s, int sidx) {
+    return round_owner_insert(c, sidx, c->stage_entries, s.stream);
+}
+
+int issue_resolve(ctmr_ctx* c, Stage& s, int sidx, const Slice& sl) {
+    const uint64_t cnt = sl.hi - sl.lo;
+    if (cnt) CU(c, launch_resolve(c->st, s.keys, cnt, s.slot_of, s.pair_slot, s.was_unknown, s.stream));
+    int rc = round_owner_resolve(c, sidx, c->stage_entries, s.stream);
+    if (rc) return rc;
+    if (cnt) CU(c, launch_resolve_pairs(c->st, s.keys, cnt, s.pair_slot, s.was_unknown, s.first, s.stream));
+    rc = round_owner_pairs(c, sidx, c->stage_entries, s.stream);
+    if (rc) return rc;
+    CU(c, cudaEventRecord(s.reduced, s.stream));
+    return CTMR_OK;
+}
+
+// string identities of the new certificates: insert (needs this rank's was_unknown bits, i.e. the pull), then -- after
+// every rank's inserts -- the read-back
+int issue_meta_insert(ctmr_ctx* c, Stage& s, const BatchArgs& a, const Slice& sl) {
     const uint64_t cnt = sl.hi - sl.lo, E = c->stage_entries;
-    if (cnt) {
-        CU(c, launch_resolve(c->st, s.keys, cnt, s.slot_of, s.pair_slot, s.was_unknown, s.stream));
-        if (want_meta)
-            CU(c, launch_meta_insert(c->st, s.blob - a.offsets[sl.lo], s.offsets, s.keys, cnt, s.was_unknown, s.spans, s.spans + E,
-                                     s.spans + 2 * E, s.spans + 3 * E, s.meta_slots, s.stream));
-    }
-    CU(c, cudaEventRecord(s.reduced, s.stream));  // after the string-identity insert too: the next round's read-back waits for it
+    if (cnt)
+        CU(c, launch_meta_insert(c->st, s.blob - a.offsets[sl.lo], s.offsets, s.keys, cnt, s.was_unknown, s.spans, s.spans + E,
+                                 s.spans + 2 * E, s.spans + 3 * E, s.meta_slots, s.stream));
+    CU(c, cudaEventRecord(s.meta_done, s.stream));
     return CTMR_OK;
 }
 
@@ -240,7 +265,6 @@ int issue_finish(ctmr_ctx* c, Stage& s, const BatchArgs& a, const Slice& sl, boo
     const uint64_t cnt = sl.hi - sl.lo, lo = sl.lo, E = c->stage_entries;
     const ctmr_out* out = a.out;
     if (!cnt) return CTMR_OK;
-    CU(c, launch_resolve_pairs(c->st, s.keys, cnt, s.pair_slot, s.was_unknown, s.first, s.stream));
     if (want_meta) {
         CU(c, launch_meta_resolve(c->st, s.keys, cnt, s.meta_slots, s.first_meta, s.first_meta + E, s.stream));
         if (out->issuer_name_off) CU(c, cudaMemcpyAsync(out->issuer_name_off + lo, s.spans, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
@@ -287,7 +311,7 @@ int run_rounds(ctmr_ctx** m, uint32_t W, const BatchArgs& a, const std::vector<s
         const int sidx = (int)(k % kStages);
         for (uint32_t r = 0; r < W; ++r)  // ---- upload + map + insert at the owners
             RR(r, issue_map(m[r], m[r]->stages[sidx], sidx, a, plan[k][r], map_dev[r], want_meta));
-        for (uint32_t r = 0; r < W; ++r) {  // ---- sync 1, then resolve
+        for (uint32_t r = 0; r < W; ++r) {  // ---- sync 1 (every member's appends have landed), then the owners' passes
             ctmr_ctx* c = m[r];
             Stage& s = c->stages[sidx];
             *failed = c;
@@ -295,10 +319,11 @@ int run_rounds(ctmr_ctx** m, uint32_t W, const BatchArgs& a, const std::vector<s
             for (uint32_t q = 0; q < W; ++q)
                 if (q != r) CU(c, cudaStreamWaitEvent(s.stream, m[q]->stages[sidx].mapped, 0));
             RR(r, peer_barrier(c, CH_STAGE_MAP + sidx, s.stream));
+            RR(r, issue_owner_insert(c, s, sidx));
             if (k > 0) CU(c, cudaStreamWaitEvent(s.stream, c->stages[(k - 1) % kStages].reduced, 0));  // the chain of rounds
-            RR(r, issue_resolve(c, s, a, plan[k][r], want_meta));
+            RR(r, issue_resolve(c, s, sidx, plan[k][r]));
         }
-        for (uint32_t r = 0; r < W; ++r) {  // ---- sync 2, then read-back + outputs
+        for (uint32_t r = 0; r < W; ++r) {  // ---- sync 2 (the owners have the bits ready), pull, [string identities]
             ctmr_ctx* c = m[r];
             Stage& s = c->stages[sidx];
             *failed = c;
@@ -306,6 +331,22 @@ int run_rounds(ctmr_ctx** m, uint32_t W, const BatchArgs& a, const std::vector<s
             for (uint32_t q = 0; q < W; ++q)
                 if (q != r) CU(c, cudaStreamWaitEvent(s.stream, m[q]->stages[sidx].reduced, 0));
             RR(r, peer_barrier(c, CH_STAGE_RESOLVE + sidx, s.stream));
+            RR(r, round_pull(c, sidx, c->stage_entries, s.was_unknown, s.first, s.stream));
+            if (want_meta) {
+                if (k > 0) CU(c, cudaStreamWaitEvent(s.stream, c->stages[(k - 1) % kStages].meta_done, 0));  // their own chain of rounds
+                RR(r, issue_meta_insert(c, s, a, plan[k][r]));
+            }
+        }
+        for (uint32_t r = 0; r < W; ++r) {  // ---- [sync 3: every member's string identities are in], outputs
+            ctmr_ctx* c = m[r];
+            Stage& s = c->stages[sidx];
+            *failed = c;
+            CU(c, cudaSetDevice(c->device));
+            if (want_meta) {
+                for (uint32_t q = 0; q < W; ++q)
+                    if (q != r) CU(c, cudaStreamWaitEvent(s.stream, m[q]->stages[sidx].meta_done, 0));
+                RR(r, peer_barrier(c, CH_STAGE_META + sidx, s.stream));
+            }
             RR(r, issue_finish(c, s, a, plan[k][r], want_meta, want_pem, &pem_base));
         }
     }
@@ -450,10 +491,17 @@ int ctmr_group_create(const ctmr_config* cfg, const int32_t* devices, uint32_t n
             (void)cudaGetLastError();
         }
     if (n_devices > 1) {
-        uint8_t* bases[kMaxWorld] = {};
-        for (uint32_t r = 0; r < n_devices; ++r) bases[r] = g->m[r]->shared;
+        uint8_t *bases[kMaxWorld] = {}, *xb[kMaxWorld] = {};
+        for (uint32_t r = 0; r < n_devices; ++r) {
+            cudaSetDevice(devices[r]);
+            const int rc = alloc_exchange(g->m[r], n_devices);
+            if (rc) return bail(rc, g->m[r]->err);
+            bases[r] = g->m[r]->shared;
+            xb[r] = g->m[r]->xchg;
+        }
         for (uint32_t r = 0; r < n_devices; ++r) {
             attach_views(g->m[r], bases, n_devices, r);
+            attach_exchange(g->m[r], xb, n_devices, r);
             g->m[r]->peer_mode = PEER_GROUP;
         }
     }
@@ -542,8 +590,16 @@ int ctmr_group_table_stats(ctmr_group* g, uint64_t* slots_used, uint64_t* capaci
 int ctmr_group_preload_known(ctmr_group* g, int64_t exp_hour, const uint8_t issuer_digest[32], const uint8_t* serial_blob,
                              const uint64_t* serial_offsets, uint64_t n) {
     if (!g || g->m.empty() || !issuer_digest || (n && (!serial_blob || !serial_offsets))) return CTMR_E_INVALID;
-    const int rc = preload_impl(g->m[0], exp_hour, issuer_digest, serial_blob, serial_offsets, n, g->next_index);
+    // the set's owner shard receives the serials (every table operation is local to the owner)
+    uint32_t issuer = 0;
+    bool found = false;
+    cudaSetDevice(g->m[0]->device);
+    int rc = lookup_digest(g->m[0], issuer_digest, true, &issuer, &found);
     if (rc) return group_fail(g, g->m[0], rc);
+    if (exp_hour > INT32_MAX || exp_hour < INT32_MIN) return group_fail(g, g->m[0], fail(g->m[0], CTMR_E_INVALID, "exp_hour out of range"));
+    ctmr_ctx* owner = g->m[key_owner((int32_t)exp_hour, issuer, (uint32_t)g->m.size())];
+    rc = preload_impl(owner, exp_hour, issuer_digest, serial_blob, serial_offsets, n, g->next_index);
+    if (rc) return group_fail(g, owner, rc);
     g->next_index += n;
     return CTMR_OK;
 }
@@ -579,20 +635,31 @@ int ctmr_group_reset(ctmr_group* g) {
 namespace {
 struct PeerHandle {
     char magic[8];  // "CTMRPEER"
-    cudaIpcMemHandle_t mem;
-    uint64_t table_slots, pair_slots, meta_slots, total;
-    uint32_t max_issuers, pad;
+    cudaIpcMemHandle_t mem, xchg;
+    uint64_t table_slots, pair_slots, meta_slots, total, X;
+    uint32_t max_issuers, world;
 };
 static_assert(sizeof(PeerHandle) <= CTMR_PEER_HANDLE_BYTES, "peer handle size");
 }  // namespace
 
-int ctmr_peer_export(ctmr_ctx* c, uint8_t handle_out[CTMR_PEER_HANDLE_BYTES]) {
-    if (!c || !handle_out) return fail(c, CTMR_E_INVALID, "bad argument");
+int ctmr_peer_export(ctmr_ctx* c, uint32_t world, uint8_t handle_out[CTMR_PEER_HANDLE_BYTES]) {
+    if (!c || !handle_out || world == 0 || world > kMaxWorld) return fail(c, CTMR_E_INVALID, "bad argument (1..8 ranks)");
+    if (c->peer_mode != PEER_NONE || c->group) return fail(c, CTMR_E_INVALID, "ctx already belongs to a group");
     CU(c, cudaSetDevice(c->device));
     PeerHandle h{};
     std::memcpy(h.magic, "CTMRPEER", 8);
-    const cudaError_t e = cudaIpcGetMemHandle(&h.mem, c->shared);
+    cudaError_t e = cudaIpcGetMemHandle(&h.mem, c->shared);
     if (e != cudaSuccess) return fail(c, CTMR_E_PEER, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    if (world > 1) {
+        if (c->xchg && c->px.world != world) return fail(c, CTMR_E_INVALID, "already exported for a different group size");
+        const int rc = alloc_exchange(c, world);
+        if (rc) return rc;
+        c->px.world = world;  // remembered for the check above; the views are set by ctmr_peer_attach
+        e = cudaIpcGetMemHandle(&h.xchg, c->xchg);
+        if (e != cudaSuccess) return fail(c, CTMR_E_PEER, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    h.X = c->X;
+    h.world = world;
     h.table_slots = c->st.table_mask + 1;
     h.pair_slots = c->st.pair_mask + 1;
     h.meta_slots = c->st.meta_mask + 1;
@@ -608,30 +675,43 @@ int ctmr_peer_attach(ctmr_ctx* c, uint32_t rank, uint32_t world, const uint8_t* 
     if (c->peer_mode != PEER_NONE || c->group) return fail(c, CTMR_E_INVALID, "ctx already belongs to a group");
     CU(c, cudaSetDevice(c->device));
     if (world == 1) return CTMR_OK;
-    uint8_t* bases[kMaxWorld] = {};
+    if (!c->xchg) return fail(c, CTMR_E_INVALID, "call ctmr_peer_export(ctx, world, ...) first");
+    uint8_t *bases[kMaxWorld] = {}, *xb[kMaxWorld] = {};
+    auto close_all = [&]() {
+        for (uint32_t q = 0; q < kMaxWorld; ++q) {
+            if (c->ipc_base[q]) { cudaIpcCloseMemHandle(c->ipc_base[q]); c->ipc_base[q] = nullptr; }
+            if (c->ipc_xchg[q]) { cudaIpcCloseMemHandle(c->ipc_xchg[q]); c->ipc_xchg[q] = nullptr; }
+        }
+    };
     for (uint32_t r = 0; r < world; ++r) {
         PeerHandle h;
         std::memcpy(&h, handles + (size_t)r * CTMR_PEER_HANDLE_BYTES, sizeof h);
         if (std::memcmp(h.magic, "CTMRPEER", 8) != 0) return fail(c, CTMR_E_INVALID, "not a ctmr peer handle");
         if (h.table_slots != c->st.table_mask + 1 || h.pair_slots != c->st.pair_mask + 1 || h.meta_slots != c->st.meta_mask + 1 ||
-            h.max_issuers != c->st.max_issuers || h.total != c->lay.total)
-            return fail(c, CTMR_E_INVALID, "rank " + std::to_string(r) + " was created with different capacities");
+            h.max_issuers != c->st.max_issuers || h.total != c->lay.total || h.X != c->X || h.world != world)
+            return fail(c, CTMR_E_INVALID, "rank " + std::to_string(r) + " was created with different capacities (or exported for another group size)");
         if (r == rank) {
             bases[r] = c->shared;
+            xb[r] = c->xchg;
             continue;
         }
-        void* p = nullptr;
-        const cudaError_t e = cudaIpcOpenMemHandle(&p, h.mem, cudaIpcMemLazyEnablePeerAccess);
+        void *p = nullptr, *x = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h.mem, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) {
+            c->ipc_base[r] = p;
+            e = cudaIpcOpenMemHandle(&x, h.xchg, cudaIpcMemLazyEnablePeerAccess);
+            if (e == cudaSuccess) c->ipc_xchg[r] = x;
+        }
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
-            for (uint32_t q = 0; q < r; ++q)
-                if (c->ipc_base[q]) { cudaIpcCloseMemHandle(c->ipc_base[q]); c->ipc_base[q] = nullptr; }
+            close_all();
             return fail(c, CTMR_E_PEER, "cudaIpcOpenMemHandle(rank " + std::to_string(r) + "): " + cudaGetErrorString(e));
         }
-        c->ipc_base[r] = p;
         bases[r] = static_cast<uint8_t*>(p);
+        xb[r] = static_cast<uint8_t*>(x);
     }
     attach_views(c, bases, world, rank);
+    attach_exchange(c, xb, world, rank);
     c->peer_mode = PEER_IPC;
     return CTMR_OK;
 }

@@ -5,15 +5,13 @@
 namespace ctmr {
 
 // ------------------------------------------------------------------------------------------------
-// K_insert / K_resolve / K_pairs.  Every table access goes to the OWNER of the entry's set
-// (st.peer.*[key_owner(...)]): on one GPU that is the local table with device-scope atomics, in a group it is a
-// peer's memory over NVLink with system-scope atomics.  Counting stays at the entry's home rank, so that one
-// sum over the ranks (ctmr_peer_allreduce_histogram_device / ctmr_group_issuer_counts) is exact.
+// K_insert / K_resolve / K_pairs.  Every table operation is LOCAL: a rank only ever inserts, resolves and counts
+// keys of sets it owns -- its own entries' (K_map's fused insert) and the records other ranks appended to its inbox.
+// Ownership is disjoint, so one sum over the ranks' histograms (ctmr_peer_allreduce_histogram_device /
+// ctmr_group_issuer_counts) is exact.  The same three bodies serve a plain key array (m on the host) and the inbox
+// regions of an exchange parity (blockIdx.y = source rank, record count read from device memory).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) insert_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
-                                                     uint32_t* __restrict__ slot_of) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
+__device__ __forceinline__ void insert_one(const DeviceState& st, const ctmr_key* __restrict__ keys, uint64_t j, uint32_t* __restrict__ slot_of) {
     const uint4* kr = reinterpret_cast<const uint4*>(keys + j);
     const uint4 q0 = kr[0], q1 = kr[1], q2 = kr[2], q3 = kr[3];
     if (q3.z == 0u) {  // not a Store-reaching entry
@@ -22,7 +20,13 @@ __global__ void __launch_bounds__(256) insert_kernel(DeviceState st, const ctmr_
     }
     const unsigned long long inv_idx = ~(((unsigned long long)q0.y << 32) | q0.x);
     const uint32_t body[12] = {q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y};
-    slot_of[j] = known_insert_owner(st.peer.table, st.peer.world, st.table_mask, st.error_flag, body, inv_idx);
+    slot_of[j] = known_insert<false>(st.table, st.table_mask, st.error_flag, body, inv_idx);
+}
+
+__global__ void __launch_bounds__(256) insert_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
+                                                     uint32_t* __restrict__ slot_of) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) insert_one(st, keys, j, slot_of);
 }
 
 template <bool SYS>
@@ -43,14 +47,12 @@ __device__ __forceinline__ uint32_t pair_insert(PairSlot* __restrict__ pairs, ui
     }
 }
 
-__global__ void __launch_bounds__(256) resolve_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
-                                                      const uint32_t* __restrict__ slot_of, uint32_t* __restrict__ pair_slot,
-                                                      uint8_t* __restrict__ was_unknown) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in = j < m;
-    const bool sys = st.peer.world > 1u;
+// `in` lanes hold record j; every lane of the warp takes part in the aggregation
+__device__ __forceinline__ void resolve_one(const DeviceState& st, const ctmr_key* __restrict__ keys, uint64_t j, bool in,
+                                            const uint32_t* __restrict__ slot_of, uint32_t* __restrict__ pair_slot,
+                                            uint8_t* __restrict__ was_unknown) {
     bool unknown = false;
-    uint32_t issuer = 0, owner = 0;
+    uint32_t issuer = 0;
     int32_t hour = 0;
     unsigned long long inv_idx = 0;
     if (in) {
@@ -60,31 +62,46 @@ __global__ void __launch_bounds__(256) resolve_kernel(DeviceState st, const ctmr
             inv_idx = ~(((unsigned long long)q0.y << 32) | q0.x);
             hour = (int32_t)q0.z;
             issuer = q0.w;
-            owner = sys ? key_owner(hour, issuer, st.peer.world) : 0u;
-            // I am the first sighting of this key (every insert of a lower index happened before the barrier)
-            unknown = ld_volatile_u64(&st.peer.table[owner][s].inv_first) == inv_idx;
+            // I am the first sighting of this key: every insert of a lower index happened before this pass
+            unknown = ld_volatile_u64(&st.table[s].inv_first) == inv_idx;
         }
         was_unknown[j] = unknown ? 1 : 0;
     }
     const uint32_t umask = __ballot_sync(0xffffffffu, unknown);
     uint32_t ps = 0xFFFFFFFFu;
     if (unknown) {
-        // per-issuer unique count (home rank): one atomic per distinct issuer per warp
+        // per-issuer unique count: one atomic per distinct issuer per warp
         const uint32_t peers = __match_any_sync(umask, issuer);
         if ((threadIdx.x & 31u) == (uint32_t)__ffs(peers) - 1u && issuer < st.max_issuers)
             atomicAdd(st.issuer_counts + issuer, (unsigned long long)__popc(peers));
-        // (issuer, exp_hour) slot at the set's owner: first-seen index + the set's cardinality
+        // the set's (issuer, exp_hour) slot: first-seen index + cardinality
         const unsigned long long pk = ((((unsigned long long)issuer) << 32) | (uint32_t)hour) + 1ull;
         const uint32_t same_set = __match_any_sync(umask, pk);
-        PairSlot* pairs = st.peer.pairs[owner];
-        ps = sys ? pair_insert<true>(pairs, st.pair_mask, st.error_flag, pk, inv_idx)
-                 : pair_insert<false>(pairs, st.pair_mask, st.error_flag, pk, inv_idx);
-        if (ps != 0xFFFFFFFFu && (threadIdx.x & 31u) == (uint32_t)__ffs(same_set) - 1u) {
-            if (sys) tab_add<true>(&pairs[ps].count, (unsigned long long)__popc(same_set));
-            else tab_add<false>(&pairs[ps].count, (unsigned long long)__popc(same_set));
-        }
+        ps = pair_insert<false>(st.pairs, st.pair_mask, st.error_flag, pk, inv_idx);
+        if (ps != 0xFFFFFFFFu && (threadIdx.x & 31u) == (uint32_t)__ffs(same_set) - 1u)
+            tab_add<false>(&st.pairs[ps].count, (unsigned long long)__popc(same_set));
     }
     if (in) pair_slot[j] = ps;
+}
+
+__global__ void __launch_bounds__(256) resolve_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
+                                                      const uint32_t* __restrict__ slot_of, uint32_t* __restrict__ pair_slot,
+                                                      uint8_t* __restrict__ was_unknown) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    resolve_one(st, keys, j, j < m, slot_of, pair_slot, was_unknown);
+}
+
+__device__ __forceinline__ void pairs_one(const DeviceState& st, const ctmr_key* __restrict__ keys, uint64_t j,
+                                          const uint32_t* __restrict__ pair_slot, const uint8_t* __restrict__ was_unknown,
+                                          uint8_t* __restrict__ first_issuer_hour) {
+    uint8_t first = 0;
+    const uint32_t ps = pair_slot[j];
+    if (was_unknown[j] && ps != 0xFFFFFFFFu) {
+        const uint4 q0 = reinterpret_cast<const uint4*>(keys + j)[0];
+        const unsigned long long inv_idx = ~(((unsigned long long)q0.y << 32) | q0.x);
+        first = ld_volatile_u64(&st.pairs[ps].inv_first) == inv_idx ? 1 : 0;
+    }
+    first_issuer_hour[j] = first;
 }
 
 __global__ void __launch_bounds__(256) pairs_kernel(DeviceState st, const ctmr_key* __restrict__ keys, uint64_t m,
@@ -92,16 +109,54 @@ __global__ void __launch_bounds__(256) pairs_kernel(DeviceState st, const ctmr_k
                                                     const uint8_t* __restrict__ was_unknown,
                                                     uint8_t* __restrict__ first_issuer_hour) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    uint8_t first = 0;
-    const uint32_t ps = pair_slot[j];
-    if (was_unknown[j] && ps != 0xFFFFFFFFu) {
-        const uint4 q0 = reinterpret_cast<const uint4*>(keys + j)[0];
-        const unsigned long long inv_idx = ~(((unsigned long long)q0.y << 32) | q0.x);
-        const uint32_t owner = st.peer.world > 1u ? key_owner((int32_t)q0.z, q0.w, st.peer.world) : 0u;
-        first = ld_volatile_u64(&st.peer.pairs[owner][ps].inv_first) == inv_idx ? 1 : 0;
-    }
-    first_issuer_hour[j] = first;
+    if (j < m) pairs_one(st, keys, j, pair_slot, was_unknown, first_issuer_hour);
+}
+
+// ---- the owner's side of the exchange: the same passes over the inbox regions of one parity ------------------
+__global__ void __launch_bounds__(256) inbox_insert_kernel(DeviceState st, PeerExchange px, uint32_t parity, uint32_t* __restrict__ in_slot) {
+    const uint32_t src = blockIdx.y;
+    if (src == px.rank) return;
+    const uint64_t region = ((uint64_t)parity * px.world + src) * px.X;
+    const uint64_t m = min((unsigned long long)px.X, ld_volatile_u64(px.counts[px.rank] + parity * px.world + src));
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) insert_one(st, px.inbox[px.rank] + region, j, in_slot + region);
+}
+__global__ void __launch_bounds__(256) inbox_resolve_kernel(DeviceState st, PeerExchange px, uint32_t parity,
+                                                            const uint32_t* __restrict__ in_slot, uint32_t* __restrict__ in_pair) {
+    const uint32_t src = blockIdx.y;
+    if (src == px.rank) return;
+    const uint64_t region = ((uint64_t)parity * px.world + src) * px.X;
+    const uint64_t m = min((unsigned long long)px.X, ld_volatile_u64(px.counts[px.rank] + parity * px.world + src));
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((uint64_t)blockIdx.x * blockDim.x >= m) return;  // whole block past the end (uniform: the warp collectives below stay convergent)
+    resolve_one(st, px.inbox[px.rank] + region, j, j < m, in_slot + region, in_pair + region, px.out_wu[px.rank] + region);
+}
+__global__ void __launch_bounds__(256) inbox_pairs_kernel(DeviceState st, PeerExchange px, uint32_t parity, const uint32_t* __restrict__ in_pair) {
+    const uint32_t src = blockIdx.y;
+    if (src == px.rank) return;
+    const uint64_t region = ((uint64_t)parity * px.world + src) * px.X;
+    const uint64_t m = min((unsigned long long)px.X, ld_volatile_u64(px.counts[px.rank] + parity * px.world + src));
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) pairs_one(st, px.inbox[px.rank] + region, j, in_pair + region, px.out_wu[px.rank] + region, px.out_first[px.rank] + region);
+}
+
+// ---- the source's side: region sizes to the owners, result bits back by position -------------------------------
+__global__ void publish_counts_kernel(PeerExchange px, uint32_t parity, const unsigned long long* __restrict__ cursor) {
+    const uint32_t t = threadIdx.x;
+    if (t < px.world && t != px.rank) px.counts[t][parity * px.world + px.rank] = cursor[t];  // one 8-byte peer store per owner
+}
+__global__ void __launch_bounds__(256) pull_bits_kernel(PeerExchange px, uint32_t parity, const unsigned long long* __restrict__ cursor,
+                                                        const uint32_t* __restrict__ rev, uint8_t* __restrict__ was_unknown,
+                                                        uint8_t* __restrict__ first_issuer_hour) {
+    const uint32_t owner = blockIdx.y;
+    if (owner == px.rank) return;
+    const uint64_t m = min((unsigned long long)px.X, cursor[owner]);
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint64_t at = ((uint64_t)parity * px.world + px.rank) * px.X + i;  // my region in the owner's outbox: contiguous reads
+    const uint32_t e = rev[(uint64_t)owner * px.X + i];
+    if (was_unknown) was_unknown[e] = __ldcv(px.out_wu[owner] + at);
+    if (first_issuer_hour) first_issuer_hour[e] = __ldcv(px.out_first[owner] + at);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -239,6 +294,36 @@ cudaError_t launch_resolve_pairs(const DeviceState& st, const ctmr_key* keys, ui
                                  const uint8_t* was_unknown, uint8_t* first_issuer_hour, cudaStream_t s) {
     if (!m) return cudaSuccess;
     pairs_kernel<<<blocks_for(m, 256), 256, 0, s>>>(st, keys, m, pair_slot, was_unknown, first_issuer_hour);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inbox_insert(const DeviceState& st, const PeerExchange& px, uint32_t parity, uint64_t max_per_region, uint32_t* in_slot,
+                                cudaStream_t s) {
+    if (px.world <= 1 || !max_per_region) return cudaSuccess;
+    inbox_insert_kernel<<<dim3(blocks_for(max_per_region, 256), px.world), 256, 0, s>>>(st, px, parity, in_slot);
+    return cudaGetLastError();
+}
+cudaError_t launch_inbox_resolve(const DeviceState& st, const PeerExchange& px, uint32_t parity, uint64_t max_per_region,
+                                 const uint32_t* in_slot, uint32_t* in_pair, cudaStream_t s) {
+    if (px.world <= 1 || !max_per_region) return cudaSuccess;
+    inbox_resolve_kernel<<<dim3(blocks_for(max_per_region, 256), px.world), 256, 0, s>>>(st, px, parity, in_slot, in_pair);
+    return cudaGetLastError();
+}
+cudaError_t launch_inbox_pairs(const DeviceState& st, const PeerExchange& px, uint32_t parity, uint64_t max_per_region,
+                               const uint32_t* in_pair, cudaStream_t s) {
+    if (px.world <= 1 || !max_per_region) return cudaSuccess;
+    inbox_pairs_kernel<<<dim3(blocks_for(max_per_region, 256), px.world), 256, 0, s>>>(st, px, parity, in_pair);
+    return cudaGetLastError();
+}
+cudaError_t launch_publish_counts(const PeerExchange& px, uint32_t parity, const unsigned long long* cursor, cudaStream_t s) {
+    if (px.world <= 1) return cudaSuccess;
+    publish_counts_kernel<<<1, 32, 0, s>>>(px, parity, cursor);
+    return cudaGetLastError();
+}
+cudaError_t launch_pull_bits(const PeerExchange& px, uint32_t parity, const unsigned long long* cursor, const uint32_t* rev,
+                             uint64_t max_per_region, uint8_t* was_unknown, uint8_t* first_issuer_hour, cudaStream_t s) {
+    if (px.world <= 1 || !max_per_region) return cudaSuccess;
+    pull_bits_kernel<<<dim3(blocks_for(max_per_region, 256), px.world), 256, 0, s>>>(px, parity, cursor, rev, was_unknown, first_issuer_hour);
     return cudaGetLastError();
 }
 

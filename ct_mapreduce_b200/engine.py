@@ -94,7 +94,8 @@ class GpuCertDatabase:
 
     def __init__(self, device: int = 0, table_capacity: int = 1 << 22, issuer_cn_filter: bytes | str = b"",
                  log_expired_entries: bool = False, flags: int = 0, max_issuers: int = 0, max_batch_entries: int = 0,
-                 max_batch_bytes: int = 0, pair_capacity_log2: int = 0, meta_capacity_log2: int = 0, _adopt=None):
+                 max_batch_bytes: int = 0, pair_capacity_log2: int = 0, meta_capacity_log2: int = 0, max_round_entries: int = 0,
+                 _adopt=None):
         self._lib = capi.load()
         if _adopt is not None:  # a member of a GpuCertGroup: the group owns the handle
             self._h, self.device, self.flags, self._owned = _adopt, device, flags, False
@@ -112,6 +113,7 @@ class GpuCertDatabase:
         cfg.max_issuers = max_issuers
         cfg.pair_capacity_log2 = pair_capacity_log2
         cfg.meta_capacity_log2 = meta_capacity_log2
+        cfg.max_round_entries = max_round_entries
         cfg.issuer_cn_filter = self._filter
         cfg.issuer_cn_filter_len = len(self._filter)
         cfg.log_expired_entries = int(bool(log_expired_entries))
@@ -280,9 +282,9 @@ class GpuCertDatabase:
         self._check(self._lib.ctmr_check_device(self._h, stream))
 
     # ------------------------------------------------------------------ one process per GPU: peers over CUDA IPC (ctmr_peer_*)
-    def peer_export(self) -> bytes:
+    def peer_export(self, world: int) -> bytes:
         h = (C.c_uint8 * capi.PEER_HANDLE_BYTES)()
-        self._check(self._lib.ctmr_peer_export(self._h, h))
+        self._check(self._lib.ctmr_peer_export(self._h, world, h))
         return bytes(h)
 
     def peer_attach(self, rank: int, world: int, handles: list):

@@ -38,7 +38,7 @@ def attach_peers(db, group=None):
     if world == 1:
         return rank, world
     handles = [None] * world
-    dist.all_gather_object(handles, db.peer_export(), group=group)
+    dist.all_gather_object(handles, db.peer_export(world), group=group)
     db.peer_attach(rank, world, handles)
     return rank, world
 

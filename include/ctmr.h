@@ -92,6 +92,9 @@ typedef struct ctmr_config {
     uint32_t log_expired_entries;    /* config logExpiredEntries (config/config.go:188) */
     uint32_t flags;                  /* CTMR_F_* */
     uint32_t meta_capacity_log2;     /* IssuerMetadata string-identity table (issuer DN / CRL-DP bytes), log2 slots; 0 = 20, max 26 */
+    uint64_t max_round_entries;      /* groups only: the most entries one GPU maps per round of ctmr_process_device
+                                      * (= ceil(n / CTMR_PEER_ROUNDS)); sizes the key-exchange regions (78 bytes x
+                                      * GPUs x 3 per entry).  0 = the host pipeline's stage size (max_batch_entries) */
 } ctmr_config;
 
 /* Caller-allocated per-entry outputs, each [n]; any pointer may be NULL to skip that copy-back. */
@@ -278,8 +281,9 @@ int ctmr_check_device(ctmr_ctx* ctx, void* stream);
 /* The worker pool of StartDatabaseThreads (cmd/ct-fetch/ct-fetch.go:140-145) becomes one call per drained batch:
  * the group cuts the batch into rounds of n_devices slices by entry index (entry i keeps global index
  * next_index + i, so the result equals the sequential numThreads=1 run over the batch in its given order), every
- * GPU maps its slice and inserts each key into the table of the set's owner GPU over NVLink, events separate the
- * inserts from the read-back, and the outputs land in the caller's arrays in entry order.  cfg->device is ignored;
+ * GPU maps its slice and hands each key to the set's owner GPU over NVLink, events separate the appends from the
+ * owners' insert/resolve and that from the pull of the result bits, and the outputs land in the caller's arrays in
+ * entry order.  cfg->device is ignored;
  * `devices` may name a device more than once (several shards on one GPU: how the path is tested on a 1-GPU box). */
 typedef struct ctmr_group ctmr_group;
 int ctmr_group_create(const ctmr_config* cfg, const int32_t* devices, uint32_t n_devices, ctmr_group** out);
@@ -307,8 +311,9 @@ int ctmr_group_reset(ctmr_group* g);
  * the same sequence of calls.  Inside them the ranks meet at barriers kept in peer memory (no host round trip, no
  * NCCL on the data path); the global index of entry j of rank r's round k is first_index + (k * world + r) * E + j,
  * i.e. the result equals the sequential run over the rounds in rank order (E = entries per rank and round). */
-#define CTMR_PEER_HANDLE_BYTES 128u
-int ctmr_peer_export(ctmr_ctx* ctx, uint8_t handle_out[CTMR_PEER_HANDLE_BYTES]);
+#define CTMR_PEER_HANDLE_BYTES 256u
+/* allocates this rank's key-exchange area for a group of `world` ranks and exports it together with the tables */
+int ctmr_peer_export(ctmr_ctx* ctx, uint32_t world, uint8_t handle_out[CTMR_PEER_HANDLE_BYTES]);
 int ctmr_peer_attach(ctmr_ctx* ctx, uint32_t rank, uint32_t world, const uint8_t* handles /* [world][CTMR_PEER_HANDLE_BYTES] */);
 /* barrier over the group on `stream` (device side; returns immediately) */
 int ctmr_peer_barrier_device(ctmr_ctx* ctx, void* stream);

@@ -85,10 +85,13 @@ def test_shipped_hot_kernel_is_what_design_md_says():
     assert not _sass_of("map_kernel_v1") and not _sass_of("map_dyn_kernel")
 
 
-def test_peer_atomics_are_system_scope():
-    """The table claims of a multi-GPU group are system-scope atomics (performed at the owner's L2 over NVLink)."""
-    blocks = _sass_of("insert_kernel")
-    assert blocks and any(".SYS" in b or ".STRONG.SYS" in b for b in blocks)
+def test_table_atomics_are_local_and_only_string_identities_cross_gpus():
+    """Known-certificate / (issuer, hour) table operations are device-scope atomics in the owner's own HBM (keys travel as
+    bulk records instead); only the O(issuers) string-identity inserts of a group use system-scope atomics over NVLink."""
+    ins = _sass_of("ctmr13insert_kernel") + _sass_of("ctmr19inbox_insert_kernel")
+    assert ins and all("ATOM" in b_ for b_ in ins) and not any(".SYS" in b_ for b_ in ins)
+    meta = _sass_of("ctmr18meta_insert_kernel")
+    assert meta and any(".SYS" in b_ for b_ in meta)
 
 
 def test_no_cpu_fallback_without_gpu(lib):
