@@ -93,7 +93,9 @@ __device__ __forceinline__ unsigned long long tab_load_acquire(const unsigned lo
     else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// 16 bytes of a slot that another GPU may have written: never from a stale L1 line
+// 16 bytes of a slot another SM (or, SYS, another GPU) has written: from L2 / the owner's memory, never a stale L1 line
+template <bool SYS>
+__device__ __forceinline__ uint4 ld_slot_u4(const uint4* p) { return SYS ? __ldcv(p) : __ldcg(p); }
 __device__ __forceinline__ uint4 ld_cv_u4(const uint4* p) { return __ldcv(p); }
 
 // Find-or-insert of a 48-byte key body; lowest global index wins through an atomic max on ~index.  An empty slot is
@@ -122,7 +124,7 @@ __device__ __forceinline__ uint32_t known_insert(KnownSlot* __restrict__ table, 
         if ((t & ~3ull) == (h & ~3ull)) {
             while ((t & 3ull) == 1ull) t = tab_load_acquire<SYS>(&sl->tag);  // another thread is publishing this slot
             const uint4* bp = reinterpret_cast<const uint4*>(sl->body);
-            const uint4 b0 = ld_cv_u4(bp), b1 = ld_cv_u4(bp + 1), b2 = ld_cv_u4(bp + 2);
+            const uint4 b0 = ld_slot_u4<SYS>(bp), b1 = ld_slot_u4<SYS>(bp + 1), b2 = ld_slot_u4<SYS>(bp + 2);
             const bool same = b0.x == body[0] && b0.y == body[1] && b0.z == body[2] && b0.w == body[3] && b1.x == body[4] &&
                               b1.y == body[5] && b1.z == body[6] && b1.w == body[7] && b2.x == body[8] && b2.y == body[9] &&
                               b2.z == body[10] && b2.w == body[11];

@@ -89,9 +89,11 @@ def test_table_atomics_are_local_and_only_string_identities_cross_gpus():
     """Known-certificate / (issuer, hour) table operations are device-scope atomics in the owner's own HBM (keys travel as
     bulk records instead); only the O(issuers) string-identity inserts of a group use system-scope atomics over NVLink."""
     ins = _sass_of("ctmr13insert_kernel") + _sass_of("ctmr19inbox_insert_kernel")
-    assert ins and all("ATOM" in b_ for b_ in ins) and not any(".SYS" in b_ for b_ in ins)
+    def atomics(block):
+        return [ln for ln in block.splitlines() if "ATOM" in ln or "RED." in ln]
+    assert ins and all(atomics(b_) for b_ in ins) and not any(".SYS" in ln for b_ in ins for ln in atomics(b_))
     meta = _sass_of("ctmr18meta_insert_kernel")
-    assert meta and any(".SYS" in b_ for b_ in meta)
+    assert meta and any(".SYS" in ln for b_ in meta for ln in atomics(b_))
 
 
 def test_no_cpu_fallback_without_gpu(lib):
