@@ -6,6 +6,8 @@
 package ctmr
 
 /*
+#include <stdlib.h>
+#include <string.h>
 #include "ctmr_frontend.h"
 */
 import "C"
@@ -13,6 +15,7 @@ import "C"
 import (
 	"bytes"
 	"fmt"
+	"runtime"
 	"unsafe"
 )
 
@@ -30,7 +33,7 @@ const (
 
 // RawPages accumulates get-entries response bodies in pinned memory (ctmr_host_alloc) together with the
 // spans of their leaf_input / extra_data strings.  The downloader appends each body as it arrives
-// (after LogClient's HTTP GET, before any JSON decoding) and flushes with Ctx.ProcessRaw.
+// (after LogClient's HTTP GET, before any JSON decoding) and flushes with DB.ProcessRaw.
 type RawPages struct {
 	Text      unsafe.Pointer // pinned, Cap bytes
 	Cap, Used uint64
@@ -82,24 +85,66 @@ func (p *RawPages) Append(body []byte) error {
 	return nil
 }
 
-// RawResult holds the per-entry outputs of ProcessRaw (ctmr_raw_out).
+// RawResult holds the per-entry outputs of ProcessRaw (ctmr_raw_out).  Like Result, every array C writes lives in
+// pinned C memory and the pointer table on the C heap (cgo: no Go pointer to memory holding Go pointers).
 type RawResult struct {
-	Result                  // the path's outputs, as for ProcessBatch
-	EntryStatus, EntryType  []uint8
-	TimestampMs             []uint64
-	Issuer                  []uint32
-	LeafSrc                 []uint8
-	LeafOff, LeafLen        []uint32
+	*Result                // the path's outputs, as for ProcessBatch
+	raw                    *C.ctmr_raw_out
+	EntryStatus, EntryType []uint8
+	TimestampMs            []uint64
+	Issuer                 []uint32
+	LeafSrc                []uint8
+	LeafOff, LeafLen       []uint32
+}
+
+func NewRawResult(n int, textBytes uint64) *RawResult {
+	r := &RawResult{Result: NewResult(n, textBytes/4*3)}
+	r.raw = (*C.ctmr_raw_out)(C.calloc(1, C.size_t(unsafe.Sizeof(C.ctmr_raw_out{}))))
+	C.memcpy(unsafe.Pointer(&r.raw.path), unsafe.Pointer(r.Result.out), C.size_t(unsafe.Sizeof(C.ctmr_out{}))) // C pointers only
+	var p unsafe.Pointer
+	p, r.EntryStatus = view[uint8](r.Result, n)
+	r.raw.entry_status = (*C.uint8_t)(p)
+	p, r.EntryType = view[uint8](r.Result, n)
+	r.raw.entry_type = (*C.uint8_t)(p)
+	p, r.TimestampMs = view[uint64](r.Result, n)
+	r.raw.timestamp_ms = (*C.uint64_t)(p)
+	p, r.Issuer = view[uint32](r.Result, n)
+	r.raw.issuer = (*C.uint32_t)(p)
+	p, r.LeafSrc = view[uint8](r.Result, n)
+	r.raw.leaf_src = (*C.uint8_t)(p)
+	p, r.LeafOff = view[uint32](r.Result, n)
+	r.raw.leaf_off = (*C.uint32_t)(p)
+	p, r.LeafLen = view[uint32](r.Result, n)
+	r.raw.leaf_len = (*C.uint32_t)(p)
+	return r
+}
+
+func (r *RawResult) Free() {
+	C.free(unsafe.Pointer(r.raw))
+	r.raw = nil
+	r.Result.Free()
 }
 
 // ProcessRaw = GetRawEntries' base64 decode + ct.LogEntryFromLeaf + insertCTWorker + Store decisions for
-// every entry of the accumulated pages, in page order.
-func (c *Ctx) ProcessRaw(p *RawPages, nowUnixNs int64, r *RawResult) error {
+// every entry of the accumulated pages, in page order (single-GPU ctx).
+func (d *DB) ProcessRaw(p *RawPages, nowUnixNs int64, r *RawResult) error {
 	n := len(p.LeafOff)
 	if n == 0 {
 		return nil
 	}
-	var b C.ctmr_raw_batch
+	if d.h == nil {
+		return fmt.Errorf("the wire-format front end runs on a single-GPU ctx")
+	}
+	b := (*C.ctmr_raw_batch)(C.calloc(1, C.size_t(unsafe.Sizeof(C.ctmr_raw_batch{}))))
+	defer C.free(unsafe.Pointer(b))
+	// the span arrays are flat Go slices; the struct that points at them is C memory, and the pointers are only
+	// stored for the duration of the call -> pin them (Go 1.21 runtime.Pinner) so that the store is legal
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	pin.Pin(&p.LeafOff[0])
+	pin.Pin(&p.LeafLen[0])
+	pin.Pin(&p.ExtraOff[0])
+	pin.Pin(&p.ExtraLen[0])
 	b.text = (*C.uint8_t)(p.Text)
 	b.text_bytes = C.uint64_t(p.Used)
 	b.leaf_input_off = (*C.uint64_t)(unsafe.Pointer(&p.LeafOff[0]))
@@ -108,14 +153,5 @@ func (c *Ctx) ProcessRaw(p *RawPages, nowUnixNs int64, r *RawResult) error {
 	b.extra_data_len = (*C.uint32_t)(unsafe.Pointer(&p.ExtraLen[0]))
 	b.n = C.uint64_t(n)
 	b.now_unix_ns = C.int64_t(nowUnixNs)
-	var o C.ctmr_raw_out
-	o.path = r.Result.cOut() // the same pointer table ProcessBatch fills (ctmr.go)
-	o.entry_status = (*C.uint8_t)(unsafe.Pointer(&r.EntryStatus[0]))
-	o.entry_type = (*C.uint8_t)(unsafe.Pointer(&r.EntryType[0]))
-	o.timestamp_ms = (*C.uint64_t)(unsafe.Pointer(&r.TimestampMs[0]))
-	o.issuer = (*C.uint32_t)(unsafe.Pointer(&r.Issuer[0]))
-	o.leaf_src = (*C.uint8_t)(unsafe.Pointer(&r.LeafSrc[0]))
-	o.leaf_off = (*C.uint32_t)(unsafe.Pointer(&r.LeafOff[0]))
-	o.leaf_len = (*C.uint32_t)(unsafe.Pointer(&r.LeafLen[0]))
-	return c.err(C.ctmr_process_raw(c.h, &b, &o), "ctmr_process_raw")
+	return d.err(C.ctmr_process_raw(d.h, b, r.raw), "ctmr_process_raw")
 }
