@@ -287,7 +287,7 @@ def main():
     n = args.entries or wl["n"]
     K, W = args.steps, args.warmup
     flags = capi.F_NO_FINGERPRINT if args.no_fingerprint else 0
-    R = capi.PEER_ROUNDS
+    R = capi.peer_rounds()
 
     def barrier():
         if world > 1:
@@ -454,7 +454,7 @@ def main():
     sha_gbs_kernel = total_bytes / (map_ms / 1e3) / 1e9
     # measured INT-pipe ceiling of the fingerprint on this GPU: register-only SHA-256 at K_map's occupancy
     int_ceiling_gbs = db.sha256_ceiling(iters=2000, rolled=True, ctas_per_sm=2)[0] if not args.no_fingerprint else None
-    map_launches = R if (world > 1 or n >= (1 << 21)) else (2 if n >= (1 << 18) else 1)
+    map_launches = R if world > 1 else (8 if n >= (1 << 21) else (2 if n >= (1 << 18) else 1))
     # per round: len_order (3 kernels) + K_map + resolve + pairs; N>1 adds 2 barrier kernels per round, 2 around the reset,
     # and barrier + sum + barrier for the histogram all-reduce
     launches_per_step = map_launches * 6 + (map_launches * 2 + 2 + 3 if world > 1 else 0)

@@ -245,6 +245,11 @@ int round_pull(ctmr_ctx* c, int parity, uint64_t maxr, uint8_t* was_unknown, uin
     return CTMR_OK;
 }
 
+uint32_t peer_rounds() {
+    static const int r = env_int("CTMR_PEER_ROUNDS", (int)CTMR_PEER_ROUNDS);
+    return (uint32_t)(r < 1 ? 1 : (r > kMaxRounds ? kMaxRounds : r));
+}
+
 int peer_barrier(ctmr_ctx* c, uint32_t channel, cudaStream_t s) {
     if (c->peer_mode != PEER_IPC) return CTMR_OK;
     CU(c, launch_peer_barrier(c->pf, channel, ++c->epoch[channel], c->st.error_flag, s));
@@ -543,12 +548,15 @@ void ctmr_destroy(ctmr_ctx* c) {
     cudaFree(c->shared); cudaFree(c->small_dev);
     cudaFree(c->issuer_map_dev); cudaFree(c->keys_scratch); cudaFree(c->slot_scratch); cudaFree(c->pair_scratch);
     cudaFree(c->bits_scratch); cudaFree(c->meta_scratch); cudaFree(c->order_scratch); cudaFree(c->len_hist);
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < kMaxRounds; ++k) {
         cudaFree(c->len_hist_sub[k]);
         if (c->ev_map0[k]) cudaEventDestroy(c->ev_map0[k]);
         if (c->ev_map1[k]) cudaEventDestroy(c->ev_map1[k]);
         if (c->ev_red1[k]) cudaEventDestroy(c->ev_red1[k]);
+        if (c->ev_tok[k]) cudaEventDestroy(c->ev_tok[k]);
     }
+    if (c->ev_join_a2) cudaEventDestroy(c->ev_join_a2);
+    if (c->stream_a2) cudaStreamDestroy(c->stream_a2);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join_a) cudaEventDestroy(c->ev_join_a);
     if (c->ev_join_b) cudaEventDestroy(c->ev_join_b);
@@ -778,14 +786,17 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
     }
     if (!c->stream_a) {
         CU(c, cudaStreamCreateWithFlags(&c->stream_a, cudaStreamNonBlocking));
+        CU(c, cudaStreamCreateWithFlags(&c->stream_a2, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&c->ev_join_a2, cudaEventDisableTiming));
         CU(c, cudaStreamCreateWithFlags(&c->stream_b, cudaStreamNonBlocking));
         CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&c->ev_join_a, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&c->ev_join_b, cudaEventDisableTiming));
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < kMaxRounds; ++k) {
             CU(c, cudaEventCreate(&c->ev_map0[k]));
             CU(c, cudaEventCreate(&c->ev_map1[k]));
             CU(c, cudaEventCreate(&c->ev_red1[k]));
+            CU(c, cudaEventCreateWithFlags(&c->ev_tok[k], cudaEventDisableTiming));
             CU(c, cudaMalloc(&c->len_hist_sub[k], 256 * sizeof(unsigned int)));
         }
         for (cudaEvent_t& e : c->ev_pulled) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -803,15 +814,19 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
     const bool coll = c->peer_mode == PEER_IPC && world > 1;
     if (c->peer_mode == PEER_GROUP && world > 1)
         return fail(c, CTMR_E_INVALID, "members of an in-process group are driven through ctmr_group_process_batch");
-    const int nsub = coll ? (int)CTMR_PEER_ROUNDS : (b->n >= (1u << 21) ? 4 : (b->n >= (1u << 18) ? 2 : 1));
+    static const int rounds_env = env_int("CTMR_DEVICE_ROUNDS", 0);   // experiments: rounds of the single-GPU call
+    static const int map_streams = env_int("CTMR_MAP_STREAMS", 2);    // K_map launches alternate between two streams
+    int nsub = coll ? (int)peer_rounds() : (b->n >= (1u << 21) ? 8 : (b->n >= (1u << 18) ? 2 : 1));
+    if (!coll && rounds_env > 0 && b->n >= (1u << 18)) nsub = rounds_env > kMaxRounds ? kMaxRounds : rounds_env;
     const uint64_t per_round = (b->n + nsub - 1) / nsub;
     if (coll && per_round > c->px.X)
-        return fail(c, CTMR_E_BATCH_TOO_LARGE, "entries per round exceed the key-exchange regions: raise config.max_round_entries to ceil(n / CTMR_PEER_ROUNDS)");
+        return fail(c, CTMR_E_BATCH_TOO_LARGE, "entries per round exceed the key-exchange regions: raise config.max_round_entries to ceil(n / ctmr_peer_rounds())");
     ctmr_key* keys = o->keys ? o->keys : c->keys_scratch;
     uint8_t* wu = o->was_unknown ? o->was_unknown : c->bits_scratch;
     uint8_t* fi = o->first_issuer_hour ? o->first_issuer_hour : c->bits_scratch + b->n;
     CU(c, cudaEventRecord(c->ev_fork, user));
     CU(c, cudaStreamWaitEvent(c->stream_a, c->ev_fork, 0));
+    CU(c, cudaStreamWaitEvent(c->stream_a2, c->ev_fork, 0));
     CU(c, cudaStreamWaitEvent(c->stream_b, c->ev_fork, 0));
     for (int k = 0; k < nsub; ++k) {
         uint64_t lo, hi;
@@ -840,24 +855,27 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
         so.issuer_name_len = o->issuer_name_len ? o->issuer_name_len + lo : nullptr;
         so.crldp_off = o->crldp_off ? o->crldp_off + lo : nullptr;
         so.crldp_len = o->crldp_len ? o->crldp_len + lo : nullptr;
-        const int parity = k & 1;
+        const int parity = k % (int)kParities;
+        // consecutive K_map launches on alternating streams: the next launch's CTAs fill the SMs the previous one's
+        // draining tail leaves idle (a persistent grid ends with its slowest warps)
+        cudaStream_t sa = (map_streams > 1 && (k & 1)) ? c->stream_a2 : c->stream_a;
         const bool fused = c->fuse_insert || world > 1;   // a group always fuses: the routing happens in K_map's epilogue
         MapParams p;
         fill_map_params(c, &sb, &so, p, 3, fused ? c->slot_scratch + lo : nullptr, parity);
-        if (world > 1 && k >= 2) CU(c, cudaStreamWaitEvent(c->stream_a, c->ev_pulled[parity], 0));  // the parity's regions are free again
-        CU(c, cudaEventRecord(c->ev_map0[k], c->stream_a));
-        rc = round_begin(c, parity, c->stream_a);
+        if (world > 1 && k >= (int)kParities) CU(c, cudaStreamWaitEvent(sa, c->ev_pulled[parity], 0));  // the parity's regions are free again
+        CU(c, cudaEventRecord(c->ev_map0[k], sa));
+        rc = round_begin(c, parity, sa);
         if (rc) return rc;
         if (c->bucket_by_length && cnt > 64 && p.sha256) {
-            CU(c, launch_len_order(sb.offsets, sb.lens, cnt, sb.blob_bytes, c->len_hist_sub[k], c->order_scratch + lo, c->stream_a));
+            CU(c, launch_len_order(sb.offsets, sb.lens, cnt, sb.blob_bytes, c->len_hist_sub[k], c->order_scratch + lo, sa));
             p.order = c->order_scratch + lo;
         }
-        CU(c, launch_map(p, c->sm_count, c->stream_a));
-        CU(c, cudaEventRecord(c->ev_map1[k], c->stream_a));
-        rc = round_publish(c, parity, c->stream_a);  // region sizes to the owners (outside K_map's timed bracket)
+        CU(c, launch_map(p, c->sm_count, sa));
+        CU(c, cudaEventRecord(c->ev_map1[k], sa));
+        rc = round_publish(c, parity, sa);  // region sizes to the owners (outside K_map's timed bracket)
         if (rc) return rc;
-        CU(c, cudaEventRecord(c->ev_join_a, c->stream_a));   // ordering token: K_map + the published sizes
-        CU(c, cudaStreamWaitEvent(c->stream_b, c->ev_join_a, 0));
+        CU(c, cudaEventRecord(c->ev_tok[k], sa));   // ordering token: K_map + the published sizes
+        CU(c, cudaStreamWaitEvent(c->stream_b, c->ev_tok[k], 0));
         cudaStream_t sbm = c->stream_b;
         if (!fused) CU(c, launch_insert(c->st, keys + lo, cnt, c->slot_scratch + lo, sbm));
         rc = peer_barrier(c, CH_DEV_MAP, sbm);  // every rank's appends of rounds <= k have landed in the owners' inboxes
@@ -884,6 +902,9 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
         CU(c, cudaEventRecord(c->ev_red1[k], c->stream_b));
     }
     c->last_sub = nsub;
+    c->last_map_streams = map_streams > 1 ? 2 : 1;
+    CU(c, cudaEventRecord(c->ev_join_a2, c->stream_a2));
+    CU(c, cudaStreamWaitEvent(user, c->ev_join_a2, 0));
     CU(c, cudaEventRecord(c->ev_join_a, c->stream_a));
     CU(c, cudaEventRecord(c->ev_join_b, c->stream_b));
     CU(c, cudaStreamWaitEvent(user, c->ev_join_a, 0));
@@ -893,14 +914,28 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
 
 /* CUDA-event timings of the last ctmr_process_device call (after the caller synchronised):
  * map_ms = sum of the K_map stage durations on their stream, total_ms = first map start -> last reduce end */
+uint32_t ctmr_peer_rounds(void) { return peer_rounds(); }
+
 int ctmr_profile_last(ctmr_ctx* c, float* map_ms, float* total_ms) {
     if (!c || c->last_sub <= 0) return fail(c, CTMR_E_INVALID, "no ctmr_process_device call to report");
     CU(c, cudaSetDevice(c->device));
     float m = 0.f, t = 0.f;
-    for (int k = 0; k < c->last_sub; ++k) {
-        float d = 0.f;
-        CU(c, cudaEventElapsedTime(&d, c->ev_map0[k], c->ev_map1[k]));
-        m += d;
+    if (c->last_map_streams > 1) {
+        // launches overlap (alternating streams): K_map's time is the span from the first launch's start to the last one's end,
+        // during which some K_map CTA is always resident
+        float best = 0.f;
+        for (int k = 0; k < c->last_sub; ++k) {
+            float d = 0.f;
+            CU(c, cudaEventElapsedTime(&d, c->ev_map0[0], c->ev_map1[k]));
+            best = d > best ? d : best;
+        }
+        m = best;
+    } else {
+        for (int k = 0; k < c->last_sub; ++k) {
+            float d = 0.f;
+            CU(c, cudaEventElapsedTime(&d, c->ev_map0[k], c->ev_map1[k]));
+            m += d;
+        }
     }
     CU(c, cudaEventElapsedTime(&t, c->ev_map0[0], c->ev_red1[c->last_sub - 1]));
     if (map_ms) *map_ms = m;

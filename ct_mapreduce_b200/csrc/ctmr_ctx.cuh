@@ -21,10 +21,16 @@ using namespace ctmr;
 namespace ctmr_host {
 
 constexpr int kStages = 3;                      // host-API pipeline depth
+constexpr int kMaxRounds = 16;                  // rounds of one ctmr_process_device call
 constexpr uint64_t kStageEntries = 1ull << 18;  // entries per pipeline stage
 constexpr uint64_t kStageBytes = 768ull << 20;  // leaf bytes per pipeline stage
 
 extern thread_local std::string g_create_error;
+
+inline int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
 
 // device side of the PEM output (ctmr_out.pem): one per host-pipeline stage and one for the front end
 struct PemStage {
@@ -159,7 +165,7 @@ struct ctmr_ctx {
     unsigned long long* cursors = nullptr;  // [kParities][kMaxWorld] records appended per owner (local)
     uint32_t* rev = nullptr;                // [kParities][world][X] inbox position -> entry
     uint32_t *in_slot = nullptr, *in_pair = nullptr;  // [kParities][world][X] owner-side scratch of the inbox records
-    cudaEvent_t ev_pulled[2] = {};          // ctmr_process_device: round k's bits pulled (its exchange parity may be reused)
+    cudaEvent_t ev_pulled[kParities] = {};  // ctmr_process_device: round k's bits pulled (its exchange parity may be reused)
     unsigned long long epoch[kPeerChannels] = {};
     struct ctmr_group* group = nullptr;    // set when the ctx is a member of an in-process group
     // issuer memo on the host (the registry itself is on the device): DER -> index, digest -> index, index -> digest
@@ -181,11 +187,11 @@ struct ctmr_ctx {
     bool bucket_by_length = true;
     bool fuse_insert = true;
     // ctmr_process_device pipelines map (stream A) against reduce (stream B) over kSub sub-batches
-    cudaStream_t stream_a = nullptr, stream_b = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join_a = nullptr, ev_join_b = nullptr;
-    cudaEvent_t ev_map0[8] = {}, ev_map1[8] = {}, ev_red1[8] = {};
-    int last_sub = 0;
-    unsigned int* len_hist_sub[8] = {};
+    cudaStream_t stream_a = nullptr, stream_a2 = nullptr, stream_b = nullptr;  // K_map alternates between a and a2
+    cudaEvent_t ev_fork = nullptr, ev_join_a = nullptr, ev_join_a2 = nullptr, ev_join_b = nullptr;
+    cudaEvent_t ev_map0[kMaxRounds] = {}, ev_map1[kMaxRounds] = {}, ev_red1[kMaxRounds] = {}, ev_tok[kMaxRounds] = {};
+    int last_sub = 0, last_map_streams = 1;
+    unsigned int* len_hist_sub[kMaxRounds] = {};
     unsigned long long* small_dev = nullptr;  // [128] private counters / cursors / results (error flag at +73)
     FrontEnd* fe = nullptr;
     std::string err;
@@ -234,6 +240,7 @@ int upload_issuer_map(ctmr_ctx* c, const uint32_t* dense, uint32_t n);
 int preload_impl(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], const uint8_t* serial_blob, const uint64_t* serial_offsets,
                  uint64_t n, uint64_t first_index);
 int ensure_stages(ctmr_ctx* c);
+uint32_t peer_rounds();   // rounds of the collective ctmr_process_device (CTMR_PEER_ROUNDS, env override for experiments)
 void pem_free(PemStage& ps);
 void stages_destroy(ctmr_ctx* c);
 int pem_ensure(ctmr_ctx* c, PemStage& ps, uint64_t entries, uint64_t der_bytes);

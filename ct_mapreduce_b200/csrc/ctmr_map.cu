@@ -294,9 +294,9 @@ __global__ void __launch_bounds__(WARPS * 32) map_stream_kernel(const __grid_con
                 }
             }
             if (c + 2u < iters) issue(c + 2u);
-            else if (LOADER == 0) cp_async_commit();  // keep "newest group = the one after chunk c+1" true at the tail
+            else if (LOADER != 1) cp_async_commit();  // keep "newest group = the one after chunk c+1" true at the tail
         }
-        if (LOADER == 0) cp_async_wait<0>();
+        if (LOADER != 1) cp_async_wait<0>();
 
         // ---- certIsFilteredOut + Store preconditions, in the reference's order
         if (act) {

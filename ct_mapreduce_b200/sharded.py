@@ -43,20 +43,22 @@ def attach_peers(db, group=None):
     return rank, world
 
 
-def round_entries(n: int, rounds: int = capi.PEER_ROUNDS) -> int:
+def round_entries(n: int, rounds: int = 0) -> int:
     """E of the collective ctmr_process_device: entries per rank and round (every rank passes the same n)."""
-    return -(-n // rounds)
+    return -(-n // (rounds or capi.peer_rounds()))
 
 
-def call_index_span(n: int, world: int, rounds: int = capi.PEER_ROUNDS) -> int:
+def call_index_span(n: int, world: int, rounds: int = 0) -> int:
     """How far a collective ctmr_process_device call advances the global index (its next call's first_index)."""
+    rounds = rounds or capi.peer_rounds()
     return world * rounds * round_entries(n, rounds)
 
 
-def sequential_order(n: int, world: int, rounds: int = capi.PEER_ROUNDS):
+def sequential_order(n: int, world: int, rounds: int = 0):
     """The order in which the sequential reference (numThreads=1) would have to see the entries of one collective
     call for its result to equal the group's: rounds in order, inside a round the ranks in order, inside a rank's
     slice the entries in order.  Yields (rank, lo, hi) slices of each rank's local batch [0, n)."""
+    rounds = rounds or capi.peer_rounds()
     e = round_entries(n, rounds)
     for k in range(rounds):
         lo, hi = min(n, k * e), min(n, (k + 1) * e)

@@ -320,8 +320,10 @@ int ctmr_peer_barrier_device(ctmr_ctx* ctx, void* stream);
 /* all-reduce(sum) of [per-issuer unique counts || status counters] over peer memory, bracketed by barriers: the
  * merge of the per-GPU histograms at the end of a chunk.  Device buffers, uint64 [n_slots] and [CTMR_ST__COUNT]. */
 int ctmr_peer_allreduce_histogram_device(ctmr_ctx* ctx, uint64_t* counts_dst, uint32_t n_slots, uint64_t* status_dst, void* stream);
-/* entries per rank and round of the collective ctmr_process_device (it always runs CTMR_PEER_ROUNDS rounds) */
-#define CTMR_PEER_ROUNDS 4u
+/* the collective ctmr_process_device always runs ctmr_peer_rounds() rounds (CTMR_PEER_ROUNDS unless the environment
+ * variable of the same name overrides it for experiments; identical on every rank) */
+#define CTMR_PEER_ROUNDS 8u
+uint32_t ctmr_peer_rounds(void);
 
 /* ---- host placement -------------------------------------------------------------------------------- */
 /* Binds the calling thread to the CPUs of the NUMA node `device` hangs off (sysfs), so that pinned buffers it
