@@ -29,7 +29,7 @@ EXPORTS = [
     "ctmr_abi_version", "ctmr_create", "ctmr_destroy", "ctmr_last_error", "ctmr_host_alloc", "ctmr_host_free",
     "ctmr_register_issuers", "ctmr_issuer_digest", "ctmr_issuer_count", "ctmr_process_batch", "ctmr_issuer_counts",
     "ctmr_set_cardinality", "ctmr_status_counters", "ctmr_table_stats", "ctmr_map_device", "ctmr_reduce_device",
-    "ctmr_process_device", "ctmr_partition_keys_device", "ctmr_partition_keys_fixed_device", "ctmr_scatter_bits_device", "ctmr_read_histogram_device",
+    "ctmr_process_device", "ctmr_read_histogram_device",
     "ctmr_check_device", "ctmr_reset_device", "ctmr_profile_last", "ctmr_preload_known", "ctmr_snapshot_size",
     "ctmr_snapshot_save", "ctmr_snapshot_load", "ctmr_evict_expired", "ctmr_sha256_ceiling_device", "ctmr_synth_offsets_device", "ctmr_synth_write_device", "ctmr_synth_truth_device", "ctmr_synth_issuers_host", "ctmr_synth_raw_pages_host",
     "ctmr_process_raw", "ctmr_frontend_profile_last",  # include/ctmr_frontend.h
@@ -147,9 +147,6 @@ def load():
     L.ctmr_map_device.argtypes = [vp, C.POINTER(DevBatch), C.POINTER(DevOut), vp]
     L.ctmr_reduce_device.argtypes = [vp, vp, u64, vp, vp, vp]
     L.ctmr_process_device.argtypes = [vp, C.POINTER(DevBatch), C.POINTER(DevOut), vp]
-    L.ctmr_partition_keys_device.argtypes = [vp, vp, u64, u32, vp, vp, vp, vp]
-    L.ctmr_partition_keys_fixed_device.argtypes = [vp, vp, u64, u32, u64, vp, vp, vp, vp]
-    L.ctmr_scatter_bits_device.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp]
     L.ctmr_read_histogram_device.argtypes = [vp, vp, u32, vp, vp]
     L.ctmr_check_device.argtypes = [vp, vp]
     L.ctmr_reset_device.argtypes = [vp, vp]

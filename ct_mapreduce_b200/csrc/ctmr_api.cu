@@ -943,34 +943,6 @@ int ctmr_profile_last(ctmr_ctx* c, float* map_ms, float* total_ms) {
     return CTMR_OK;
 }
 
-int ctmr_partition_keys_device(ctmr_ctx* c, const ctmr_key* keys, uint64_t n, uint32_t world, ctmr_key* by_owner,
-                               uint32_t* src_pos, uint64_t* owner_counts, void* stream) {
-    if (!c || world == 0 || world > 64 || !owner_counts || (n && (!keys || !by_owner || !src_pos)))
-        return fail(c, CTMR_E_INVALID, "bad argument");
-    CU(c, cudaSetDevice(c->device));
-    CU(c, launch_partition(keys, n, world, by_owner, src_pos, reinterpret_cast<unsigned long long*>(owner_counts),
-                           c->small_dev, stream ? (cudaStream_t)stream : c->stream));
-    return CTMR_OK;
-}
-
-int ctmr_partition_keys_fixed_device(ctmr_ctx* c, const ctmr_key* keys, uint64_t n, uint32_t world, uint64_t capacity,
-                                     ctmr_key* by_owner, uint32_t* src_pos, int32_t* overflow, void* stream) {
-    if (!c || world == 0 || world > 64 || capacity == 0 || !by_owner || !src_pos || !overflow || (n && !keys))
-        return fail(c, CTMR_E_INVALID, "bad argument");
-    CU(c, cudaSetDevice(c->device));
-    CU(c, launch_partition_fixed(keys, n, world, capacity, by_owner, src_pos, overflow, c->small_dev,
-                                 stream ? (cudaStream_t)stream : c->stream));
-    return CTMR_OK;
-}
-
-int ctmr_scatter_bits_device(ctmr_ctx* c, const uint8_t* a, const uint8_t* b, const uint32_t* src_pos, uint64_t m,
-                             uint8_t* a_dst, uint8_t* b_dst, void* stream) {
-    if (!c || (m && (!a || !b || !src_pos))) return fail(c, CTMR_E_INVALID, "bad argument");
-    CU(c, cudaSetDevice(c->device));
-    CU(c, launch_scatter_bits(a, b, src_pos, m, a_dst, b_dst, stream ? (cudaStream_t)stream : c->stream));
-    return CTMR_OK;
-}
-
 int ctmr_read_histogram_device(ctmr_ctx* c, uint64_t* counts_dst, uint32_t n_slots, uint64_t* status_dst, void* stream) {
     if (!c || n_slots > c->st.max_issuers) return fail(c, CTMR_E_INVALID, "bad argument");
     CU(c, cudaSetDevice(c->device));

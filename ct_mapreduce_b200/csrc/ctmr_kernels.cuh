@@ -210,13 +210,6 @@ cudaError_t launch_evict_compact(const DeviceState& st, int64_t now_sec, KnownSl
 cudaError_t launch_evict_reinsert(const DeviceState& st, const KnownSlot* keep, uint64_t n, cudaStream_t s);
 cudaError_t launch_cardinality(const DeviceState& st, int32_t exp_hour, uint32_t issuer, unsigned long long* out,
                                cudaStream_t s);
-cudaError_t launch_partition(const ctmr_key* keys, uint64_t n, uint32_t world, ctmr_key* keys_by_owner,
-                             uint32_t* src_pos, unsigned long long* owner_counts, unsigned long long* cursors,
-                             cudaStream_t s);
-cudaError_t launch_partition_fixed(const ctmr_key* keys, uint64_t n, uint32_t world, uint64_t capacity, ctmr_key* keys_by_owner,
-                                   uint32_t* src_pos, int* overflow, unsigned long long* cursors, cudaStream_t s);
-cudaError_t launch_scatter_bits(const uint8_t* a, const uint8_t* b, const uint32_t* src_pos, uint64_t m, uint8_t* a_dst,
-                                uint8_t* b_dst, cudaStream_t s);
 
 // ---- CT wire-format front end (ctmr_frontend.cu, include/ctmr_frontend.h) ------------------------
 #define CTMR_ISSUER_UNRESOLVED 0xFFFFFFFDu  // internal: Chain[0] present, dense index not looked up yet

@@ -1,5 +1,6 @@
 // ctmr_reduce.cu -- the reduce half: known-certificate table insert / resolve, (issuer, hour) first-seen,
-// IssuerMetadata string identities, issuer preparation, set cardinality, multi-GPU key partition.
+// IssuerMetadata string identities, issuer preparation, set cardinality, the owner / source passes of the multi-GPU key
+// exchange, the issuer registry, the cross-process barrier and the histogram merge.
 #include "ctmr_common.cuh"
 
 namespace ctmr {
@@ -593,108 +594,4 @@ cudaError_t launch_hist_sum(const PeerFlags& pf, uint32_t n_slots, unsigned long
     return cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------------------------
-// multi-GPU routing helpers
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) owner_count_kernel(const ctmr_key* __restrict__ keys, uint64_t n, uint32_t world,
-                                                          unsigned long long* __restrict__ counts) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = false;
-    uint32_t owner = 0;
-    if (j < n) {
-        const uint4 q0 = reinterpret_cast<const uint4*>(keys + j)[0];
-        valid = reinterpret_cast<const uint4*>(keys + j)[3].z != 0u;
-        owner = key_owner((int32_t)q0.z, q0.w, world);
-    }
-    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-        const uint32_t peers = __match_any_sync(vmask, owner);
-        if ((threadIdx.x & 31u) == (uint32_t)__ffs(peers) - 1u) atomicAdd(counts + owner, (unsigned long long)__popc(peers));
-    }
-}
-
-__global__ void owner_scan_kernel(const unsigned long long* counts, uint32_t world, unsigned long long* cursors) {
-    unsigned long long acc = 0;
-    for (uint32_t w = 0; w < world; ++w) {
-        cursors[w] = acc;
-        acc += counts[w];
-    }
-}
-
-// `limit` = 0: buckets are contiguous (cursors start at the scanned counts).  `limit` > 0: bucket w owns the fixed
-// range [w*limit, (w+1)*limit) (cursors start at w*limit); a record that does not fit raises *overflow and is dropped.
-__global__ void __launch_bounds__(256) owner_scatter_kernel(const ctmr_key* __restrict__ keys, uint64_t n, uint32_t world,
-                                                            unsigned long long* __restrict__ cursors,
-                                                            ctmr_key* __restrict__ out, uint32_t* __restrict__ src_pos,
-                                                            uint64_t limit, int* __restrict__ overflow) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = false;
-    uint32_t owner = 0;
-    uint4 q0, q1, q2, q3;
-    if (j < n) {
-        const uint4* kr = reinterpret_cast<const uint4*>(keys + j);
-        q0 = kr[0]; q1 = kr[1]; q2 = kr[2]; q3 = kr[3];
-        valid = q3.z != 0u;
-        owner = key_owner((int32_t)q0.z, q0.w, world);
-    }
-    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-        const uint32_t peers = __match_any_sync(vmask, owner);
-        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
-        unsigned long long base = 0;
-        if ((threadIdx.x & 31u) == leader) base = atomicAdd(cursors + owner, (unsigned long long)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        const uint64_t dst = base + __popc(peers & ((1u << (threadIdx.x & 31u)) - 1u));
-        if (limit && dst >= (uint64_t)(owner + 1u) * limit) {
-            atomicExch(overflow, 1);
-            return;
-        }
-        uint4* o = reinterpret_cast<uint4*>(out + dst);
-        o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3;
-        src_pos[dst] = (uint32_t)j;
-    }
-}
-
-cudaError_t launch_partition(const ctmr_key* keys, uint64_t n, uint32_t world, ctmr_key* keys_by_owner, uint32_t* src_pos,
-                             unsigned long long* owner_counts, unsigned long long* cursors, cudaStream_t s) {
-    cudaError_t err = cudaMemsetAsync(owner_counts, 0, sizeof(unsigned long long) * world, s);
-    if (err != cudaSuccess || !n) return err;
-    owner_count_kernel<<<blocks_for(n, 256), 256, 0, s>>>(keys, n, world, owner_counts);
-    owner_scan_kernel<<<1, 1, 0, s>>>(owner_counts, world, cursors);
-    owner_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(keys, n, world, cursors, keys_by_owner, src_pos, 0, nullptr);
-    return cudaGetLastError();
-}
-
-__global__ void owner_fixed_init_kernel(uint32_t world, uint64_t capacity, unsigned long long* cursors) {
-    for (uint32_t w = threadIdx.x; w < world; w += blockDim.x) cursors[w] = (unsigned long long)w * capacity;
-}
-
-// Fixed-capacity routing: no bucket size ever has to reach the host (the all-to-all uses equal splits).
-cudaError_t launch_partition_fixed(const ctmr_key* keys, uint64_t n, uint32_t world, uint64_t capacity, ctmr_key* keys_by_owner,
-                                   uint32_t* src_pos, int* overflow, unsigned long long* cursors, cudaStream_t s) {
-    cudaError_t err = cudaMemsetAsync(keys_by_owner, 0, (size_t)world * capacity * sizeof(ctmr_key), s);  // valid = 0 everywhere
-    if (err == cudaSuccess) err = cudaMemsetAsync(src_pos, 0xFF, (size_t)world * capacity * sizeof(uint32_t), s);
-    if (err != cudaSuccess || !n) return err;
-    owner_fixed_init_kernel<<<1, 64, 0, s>>>(world, capacity, cursors);
-    owner_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(keys, n, world, cursors, keys_by_owner, src_pos, capacity, overflow);
-    return cudaGetLastError();
-}
-
-__global__ void __launch_bounds__(256) scatter_bits_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
-                                                           const uint32_t* __restrict__ src_pos, uint64_t m,
-                                                           uint8_t* __restrict__ a_dst, uint8_t* __restrict__ b_dst) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    const uint32_t d = src_pos[j];
-    if (d == 0xFFFFFFFFu) return;  // an unused slot of the fixed-capacity layout
-    if (a_dst) a_dst[d] = a[j];
-    if (b_dst) b_dst[d] = b[j];
-}
-
-cudaError_t launch_scatter_bits(const uint8_t* a, const uint8_t* b, const uint32_t* src_pos, uint64_t m, uint8_t* a_dst,
-                                uint8_t* b_dst, cudaStream_t s) {
-    if (!m) return cudaSuccess;
-    scatter_bits_kernel<<<blocks_for(m, 256), 256, 0, s>>>(a, b, src_pos, m, a_dst, b_dst);
-    return cudaGetLastError();
-}
 }  // namespace ctmr

@@ -248,18 +248,6 @@ class GpuCertDatabase:
     def process_device(self, batch: capi.DevBatch, out: capi.DevOut, stream=None):
         self._check(self._lib.ctmr_process_device(self._h, C.byref(batch), C.byref(out), stream))
 
-    def partition_keys_device(self, keys, n: int, world: int, keys_by_owner, src_pos, owner_counts, stream=None):
-        self._check(self._lib.ctmr_partition_keys_device(self._h, capi.ptr(keys), n, world, capi.ptr(keys_by_owner),
-                                                         capi.ptr(src_pos), capi.ptr(owner_counts), stream))
-
-    def partition_keys_fixed_device(self, keys, n: int, world: int, capacity: int, keys_by_owner, src_pos, overflow, stream=None):
-        self._check(self._lib.ctmr_partition_keys_fixed_device(self._h, capi.ptr(keys), n, world, capacity, capi.ptr(keys_by_owner),
-                                                               capi.ptr(src_pos), capi.ptr(overflow), stream))
-
-    def scatter_bits_device(self, was_unknown, first, src_pos, m: int, was_unknown_dst, first_dst, stream=None):
-        self._check(self._lib.ctmr_scatter_bits_device(self._h, capi.ptr(was_unknown), capi.ptr(first), capi.ptr(src_pos), m,
-                                                       capi.ptr(was_unknown_dst), capi.ptr(first_dst), stream))
-
     def read_histogram_device(self, counts_dst, n_slots: int, status_dst=None, stream=None):
         self._check(self._lib.ctmr_read_histogram_device(self._h, capi.ptr(counts_dst), n_slots, capi.ptr(status_dst), stream))
 

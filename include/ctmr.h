@@ -250,25 +250,8 @@ int ctmr_process_device(ctmr_ctx* ctx, const ctmr_dev_batch* batch, const ctmr_d
  * map_ms = summed duration of the K_map stage (measured on the stream it ran on), total_ms = whole call */
 int ctmr_profile_last(ctmr_ctx* ctx, float* map_ms, float* total_ms);
 
-/* multi-GPU key routing: owner(key) = hash(exp_hour, issuer) mod world, i.e. one
- * Redis set lives on one GPU.  Counting-sort the valid keys by owner. */
-int ctmr_partition_keys_device(ctmr_ctx* ctx, const ctmr_key* keys, uint64_t n, uint32_t world,
-                               ctmr_key* keys_by_owner /* [n] */, uint32_t* src_pos /* [n] */,
-                               uint64_t* owner_counts /* device [world] */, void* stream);
-/* The same routing with a FIXED capacity per owner, so that no bucket size has to reach the host and the key
- * exchange can be an equal-split all-to-all: owner w's records go to keys_by_owner[w*capacity ..), unused slots
- * keep valid = 0 (the reduce kernels skip them) and src_pos = 0xFFFFFFFF (ctmr_scatter_bits_device skips them).
- * *overflow (device int32, cleared by the caller) becomes 1 if some owner had more than `capacity` records:
- * the chunk must then be routed with ctmr_partition_keys_device instead. */
-int ctmr_partition_keys_fixed_device(ctmr_ctx* ctx, const ctmr_key* keys, uint64_t n, uint32_t world, uint64_t capacity,
-                                     ctmr_key* keys_by_owner /* [world*capacity] */, uint32_t* src_pos /* [world*capacity] */,
-                                     int32_t* overflow /* device */, void* stream);
-/* scatter routed-back result bits to entry order: dst[src_pos[j]] = bits[j], j < m */
-int ctmr_scatter_bits_device(ctmr_ctx* ctx, const uint8_t* was_unknown, const uint8_t* first_issuer_hour,
-                             const uint32_t* src_pos, uint64_t m, uint8_t* was_unknown_dst,
-                             uint8_t* first_issuer_hour_dst, void* stream);
 /* copy the per-issuer histogram (uint64 [n_slots], dense index order) and the status counters
- * (uint64 [CTMR_ST__COUNT]) into device buffers, e.g. for one ncclAllReduce(sum) per chunk */
+ * (uint64 [CTMR_ST__COUNT]) of THIS GPU into device buffers (a group merges them with ctmr_peer_allreduce_histogram_device) */
 int ctmr_read_histogram_device(ctmr_ctx* ctx, uint64_t* counts_dst, uint32_t n_slots, uint64_t* status_dst,
                                void* stream);
 /* forget everything: known-certificate table, first-seen pairs, per-issuer and status counters

@@ -508,66 +508,3 @@ def test_ttl_eviction_matches_redis_expiry(eng, ora):
         # everything is past its TTL eventually
         assert db.evict_expired(1 << 40) == odb.evict_expired(1 << 40) > 0
         assert db.table_stats()[0] == 0 and not any(db.issuer_counts().values())
-
-
-def test_fixed_capacity_key_routing_on_one_gpu(eng, ora):
-    """ctmr_partition_keys_fixed_device (the sync-free form of the multi-GPU routing): layout, padding, overflow flag,
-    and that reduce + scatter over the padded buckets give the answers of the direct path."""
-    import torch
-    from ct_mapreduce_b200 import capi
-    from test_sharded_gloo import key_owner
-    n, world = 20000, 4
-    kw = dict(len_mode=1, len_lo=512, len_hi=2048, dup_mode=1)
-    cfg_o, cfg_g = ora.synth_cfg(n, **kw), capi.synth_cfg(n, **kw)
-    blob, offs, idx = ora.synth_corpus(cfg_o, 0, n)
-    iblob, ioffs = ora.synth_issuers(cfg_o)
-    want = ora.DB(README_FILTER, False).process(blob, offs, iblob, ioffs, idx, NOW_NS)
-    dev = torch.device("cuda:0")
-    dblob, doffs, didx, total = eng.synth_corpus_device(cfg_g, 0, n, dev)
-    with eng.GpuCertDatabase(table_capacity=1 << 16, issuer_cn_filter=README_FILTER, max_issuers=1024) as db:
-        db.register_issuers(iblob, ioffs)
-        status = torch.empty(n, dtype=torch.uint8, device=dev)
-        keys = torch.empty((n, 64), dtype=torch.uint8, device=dev)
-        b = capi.DevBatch()
-        b.blob, b.blob_bytes, b.offsets, b.n = dblob.data_ptr(), total, doffs.data_ptr(), n
-        b.issuer_idx, b.issuer_map, b.issuer_map_len = didx.data_ptr(), None, 0
-        b.first_index, b.now_unix_ns = 0, NOW_NS
-        db.map_device(b, capi.DevOut(status.data_ptr(), None, None, None, None, None, None, keys.data_ptr()))
-        cap = 3200
-        by_owner = torch.empty((world * cap, 64), dtype=torch.uint8, device=dev)
-        src = torch.empty(world * cap, dtype=torch.int32, device=dev)
-        over = torch.zeros(1, dtype=torch.int32, device=dev)
-        db.partition_keys_fixed_device(keys, n, world, cap, by_owner, src, over)
-        torch.cuda.synchronize()
-        assert int(over.item()) == 0
-        recs = keys.cpu().numpy().reshape(-1).view(capi.KEY_DTYPE)
-        out = by_owner.cpu().numpy().reshape(-1).view(capi.KEY_DTYPE)
-        sp = src.cpu().numpy()
-        assert np.array_equal(recs["valid"] != 0, want.status == 0)
-        owners = np.array([key_owner(int(r["exp_hour"]), int(r["issuer"]), world) if r["valid"] else -1 for r in recs])
-        for w in range(world):
-            bucket, bsrc = out[w * cap:(w + 1) * cap], sp[w * cap:(w + 1) * cap]
-            k = int((owners == w).sum())
-            assert 0 < k <= cap
-            assert sorted(bsrc[:k].tolist()) == np.nonzero(owners == w)[0].tolist()       # every record of this owner, once
-            assert all(bucket[j].tobytes() == recs[bsrc[j]].tobytes() for j in range(0, k, 37))
-            assert not bucket["valid"][k:].any() and (bsrc[k:] == -1).all()               # padding
-        # owner side over ALL buckets (as if one rank owned everything), then home again
-        ou = torch.empty(world * cap, dtype=torch.uint8, device=dev)
-        of_ = torch.empty(world * cap, dtype=torch.uint8, device=dev)
-        db.reduce_device(by_owner, world * cap, ou, of_)
-        wu = torch.zeros(n, dtype=torch.uint8, device=dev)
-        fi = torch.zeros(n, dtype=torch.uint8, device=dev)
-        db.scatter_bits_device(ou, of_, src, world * cap, wu, fi)
-        db.check_device()
-        torch.cuda.synchronize()
-        assert np.array_equal(wu.cpu().numpy(), want.was_unknown) and np.array_equal(fi.cpu().numpy(), want.first_issuer_hour)
-        assert sum(db.issuer_counts().values()) == int(want.was_unknown.sum())
-        # a capacity below the largest bucket is reported, never written past
-        small = int((owners == 0).sum()) - 1
-        by2 = torch.full((world * small + 1, 64), 0xEE, dtype=torch.uint8, device=dev)
-        src2 = torch.empty(world * small, dtype=torch.int32, device=dev)
-        over.zero_()
-        db.partition_keys_fixed_device(keys, n, world, small, by2, src2, over)
-        torch.cuda.synchronize()
-        assert int(over.item()) == 1 and (by2[world * small].cpu().numpy() == 0xEE).all()
