@@ -691,7 +691,9 @@ int ora_db_process(ora_db* db, const uint8_t* blob, const uint64_t* offsets, uin
             uint32_t k = issuer_idx[i];
             if (k == 0xFFFFFFFFu || k >= n_issuers) st = ORA_ST_NO_ISSUER;      /* ct-fetch.go:215-219 */
             else if (irec[k].status) st = ORA_ST_ISSUER_PARSE_ERR;             /* ct-fetch.go:221-225 */
-            else if (out->serial_len[i] > 39) st = ORA_ST_SERIAL_TOO_LONG;     /* GPU key-record limit */
+            /* no serial-length limit: NewSerial keeps whatever the INTEGER holds (storage/types.go:171-178).  The GPU key
+             * record holds 39 octets and DECLINES longer serials (CTMR_ST_SERIAL_TOO_LONG): a divergence of the product,
+             * pinned by tests/test_gpu_parity.py::test_long_serials_are_declined_not_misdeduplicated, not modelled here */
         }
         out->status[i] = (uint8_t)st;
         db->counters[st & 7]++;

@@ -43,7 +43,7 @@ enum {
     ORA_ST_FILTER_CN = 4,        /* ct-fetch.go:57-68  */
     ORA_ST_NO_ISSUER = 5,        /* ct-fetch.go:215-219 */
     ORA_ST_ISSUER_PARSE_ERR = 6, /* ct-fetch.go:221-225 */
-    ORA_ST_SERIAL_TOO_LONG = 7   /* documented limit of the GPU key record (39 octets) */
+    ORA_ST_SERIAL_TOO_LONG = 7   /* never produced by the oracle (the reference has no limit); the GPU path declines serials > 39 octets */
 };
 
 typedef struct ora_cert {

@@ -508,3 +508,39 @@ def test_ttl_eviction_matches_redis_expiry(eng, ora):
         # everything is past its TTL eventually
         assert db.evict_expired(1 << 40) == odb.evict_expired(1 << 40) > 0
         assert db.table_stats()[0] == 0 and not any(db.issuer_counts().values())
+
+
+def test_long_serials_are_declined_not_misdeduplicated(eng, ora):
+    """The ONE place where the product knowingly differs from the reference: a key record holds 39
+    serial octets.  The reference has no limit (storage/types.go:171-178) and the oracle follows it; the GPU path
+    DECLINES longer serials -- status CTMR_ST_SERIAL_TOO_LONG, never was_unknown, never in a set -- so that the host
+    routes exactly those entries to the stock per-entry Store (go/ctmr/gpudatabase.go).  Everything else is unchanged,
+    in both map kernels."""
+    from ct_mapreduce_b200 import capi
+    from test_oracle_properties import _cert_with_times
+    ders, long_ = [], []
+    for rep in range(2):
+        for n in (1, 20, 38, 39, 40, 41, 64, 127, 128, 300):
+            ser = bytes([0x01]) + bytes([(n * 7 + 3) & 0xFF]) * (n - 1)
+            ders.append(_cert_with_times(b"900101000000Z", b"300615123045Z", serial=ser))
+            long_.append(n > 39)
+    long_ = np.array(long_)
+    blob, offs = pack(ders)
+    iblob, ioffs = pack([ders[0]])
+    idx = np.zeros(len(ders), np.uint32)
+    want = ora.DB(b"", True).process(blob, offs, iblob, ioffs, idx, NOW_NS)
+    assert (want.status == 0).all() and want.was_unknown.tolist() == [1] * 10 + [0] * 10     # the reference stores them all
+    for flags in (0, capi.F_NO_FINGERPRINT):
+        with eng.GpuCertDatabase(log_expired_entries=True, table_capacity=1 << 12, flags=flags) as db:
+            got = db.store_batch(blob, offs, iblob, ioffs, idx, NOW_NS, want_sha=not flags)
+            sc = db.status_counters()
+            counts = db.issuer_counts()
+        assert (got.status[long_] == capi.ST_SERIAL_TOO_LONG).all() and (got.was_unknown[long_] == 0).all()
+        assert np.array_equal(got.status[~long_], want.status[~long_])
+        assert np.array_equal(got.was_unknown[~long_], want.was_unknown[~long_])
+        assert np.array_equal(got.serial_len, want.serial_len) and np.array_equal(got.serial_off, want.serial_off)
+        assert np.array_equal(got.exp_hour, want.exp_hour)
+        assert int(sc[capi.ST_SERIAL_TOO_LONG]) == int(long_.sum()) and int(sc[capi.ST_OK]) == int((~long_).sum())
+        assert sum(counts.values()) == int(want.was_unknown[~long_].sum())
+        if not flags:
+            assert np.array_equal(got.sha256, want.sha256)
