@@ -618,6 +618,45 @@ def main():
                          args.secondary_entries or 100_000_000, capi.F_NO_FINGERPRINT))
         plan.append((f"configs[3] shape: {per_gpu * world / 1e6:.0f}M entries over {world} GPU(s)", "cfg4", per_gpu, 0))
         plan.append((f"configs[4] shape: {per_gpu * world / 1e6:.0f}M mixed-size entries, 50% duplicates, over {world} GPU(s)", "cfg5", per_gpu, 0))
+        def frontend_run(n_raw):
+            """get-entries response bodies (JSON, base64 leaf_input / extra_data; 2/3 x509 entries, 1/3 precert
+            entries) through ctmr_process_raw: pinned host text in, host results out, every copy inside the timed calls."""
+            from ct_mapreduce_b200 import frontend  # noqa: F401  (span finder; the pages here come with their spans)
+            cfgr = capi.synth_cfg(n_raw, seed=SEED + 2)
+            need = lib.ctmr_synth_raw_pages_host(C.byref(cfgr), 0, n_raw, 1000, None, 0, None, None, None, None)
+            pin = capi.PinnedBuffer(need)
+            lo_, ll_ = np.zeros(n_raw, np.uint64), np.zeros(n_raw, np.uint32)
+            xo_, xl_ = np.zeros(n_raw, np.uint64), np.zeros(n_raw, np.uint32)
+            assert lib.ctmr_synth_raw_pages_host(C.byref(cfgr), 0, n_raw, 1000, pin.addr, need, capi.ptr(lo_), capi.ptr(ll_), capi.ptr(xo_),
+                                                 capi.ptr(xl_)) == need
+            text = pin.view()
+            dbr = engine.GpuCertDatabase(device=local, log_expired_entries=True, table_capacity=pow2(4 * n_raw), max_issuers=4096)
+            try:
+                fe_ms = path_ms = 0.0
+                reps = 3
+                for it in range(1 + reps):
+                    if it == 1:
+                        ts_ = time.perf_counter()
+                    r_ = dbr.store_raw_entries(text, lo_, ll_, xo_, xl_, NOW_NS)
+                    if it >= 1:
+                        f_, p_, _ = dbr.frontend_profile_last()
+                        fe_ms += f_
+                        path_ms += p_
+                dt_ = (time.perf_counter() - ts_) / reps
+                assert int((r_.entry_status == 0).sum()) == n_raw, "front end rejected synthetic entries"
+                # replays of the same pages: everything is known the second time round
+                assert int(r_.path.was_unknown.sum()) == 0
+            finally:
+                dbr.close()
+                pin.free()
+            chars = int(ll_.sum()) + int(xl_.sum())
+            return {"name": "get-entries pages through ctmr_process_raw (CT wire-format front end, SURVEY 8(f)-2)", "entries": n_raw,
+                    "value": n_raw / dt_, "unit": "entries/s", "seconds": dt_, "text_bytes": int(need), "h2d_gbs": need / dt_ / 1e9,
+                    "frontend_kernels_ms": fe_ms / reps, "frontend_kernels_entries_per_sec": n_raw / (fe_ms / reps) * 1e3,
+                    "frontend_kernels_chars_gbs": chars / (fe_ms / reps) / 1e6, "path_ms": path_ms / reps,
+                    "note": "whole calls: pinned host text in (PCIe bound: ~5 KB of base64 per entry), host results out; base64 decode, TLS "
+                            "framing, precert TBS check and Chain[0] identification on the GPU"}
+
         for tag, wn, pe, fl in plan:
             try:
                 secondary.append(stream_run(tag, wn, pe, fl))
@@ -627,6 +666,11 @@ def main():
                     torch.cuda.synchronize(dev)
                 except Exception:
                     break
+        if world == 1:
+            try:
+                secondary.append(frontend_run(min(600_000, max(20_000, (args.secondary_entries or 100_000_000) // 100))))
+            except Exception as e:  # noqa: BLE001
+                secondary.append({"name": "ctmr_process_raw", "error": f"{type(e).__name__}: {e}"[:300]})
 
     if rank == 0:
         roofline = {"bound": "int_alu" if not args.no_fingerprint else "hbm",

@@ -129,6 +129,10 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
         p.crldp_off = o->crldp_off;
         p.crldp_len = o->crldp_len;
     }
+    {
+        static const int lp = env_int("CTMR_LIGHT_PREFETCH", 0);
+        p.light_prefetch = (uint32_t)lp;
+    }
     p.status_counts = c->st.status_counts;
     p.work_counter = c->small_dev + 84 + counter_slot;  // one per pipeline stage + one for the device entry points
     p.filter = c->filter;
@@ -399,6 +403,10 @@ int ensure_frontend(ctmr_ctx* c) {
     }
     FEM(f->pad_size, (2 * E + 1) * 8); FEM(f->dec_off, (2 * E + 1) * 8); FEM(f->dec_len, 2 * E * 4); FEM(f->str_bad, 2 * E);
     FEM(f->decoded, f->cap_decoded);
+    if (cudaMemsetAsync(f->decoded, 0, f->cap_decoded, c->stream) != cudaSuccess) {  // the 16-byte padding between decoded strings is read (never consumed) by K_map's staging
+        fail(c, CTMR_E_CUDA, "front end: arena initialisation failed");
+        return bail(CTMR_E_CUDA);
+    }
     f->scan_temp_bytes = fe_scan_temp_bytes(2 * E + 1);
     FEM(f->scan_temp, f->scan_temp_bytes ? f->scan_temp_bytes : 16);
     FEM(f->entry_status, E); FEM(f->entry_type, E); FEM(f->leaf_src, E); FEM(f->timestamp, E * 8);

@@ -161,6 +161,8 @@ struct MapParams {
     uint64_t table_mask;
     int* error_flag;
     uint32_t* slot_of;
+    uint32_t light_prefetch;  // map_light_kernel: low 4 bits = leading 128-byte lines to prefetch per record, bit 4 = also the tail
+    uint32_t pad_lp;
     FilterCfg filter;
 };
 

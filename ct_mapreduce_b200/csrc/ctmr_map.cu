@@ -62,6 +62,19 @@ __global__ void __launch_bounds__(256, 4) map_light_kernel(const __grid_constant
         const bool bad_span = end < off || end > p.blob_bytes || end - off > 0x7fffffffull;
         const uint32_t L = bad_span ? 0u : (uint32_t)(end - off);
         const uint8_t* d = p.blob + off;
+        if (p.light_prefetch && L) {
+            // The walk is a pointer chase (ncu: 19 long-scoreboard stalls per issue, DRAM 25 % busy): start the lines it is
+            // going to need -- header, serial, names, validity at the front; signatureAlgorithm + signature header at the
+            // back -- before the first dependent load, so that they arrive in parallel
+            const uint8_t* base = reinterpret_cast<const uint8_t*>(reinterpret_cast<uint64_t>(d) & ~127ull);
+            const uint32_t lines = (uint32_t)((d - base) + L + 127u) >> 7;
+            const uint32_t nl = min(p.light_prefetch & 15u, lines);
+            for (uint32_t i = 0; i < nl; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 128u * i));
+            if ((p.light_prefetch & 16u) && L > 320u) {
+                const uint8_t* tail = reinterpret_cast<const uint8_t*>(reinterpret_cast<uint64_t>(d + L - 288u) & ~127ull);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(tail));
+            }
+        }
         ParsedCert pc;
         uint32_t issuer = CTMR_ISSUER_NONE;
         int64_t exp_hour = 0;
@@ -427,12 +440,27 @@ __global__ void __launch_bounds__(256) len_hist_kernel(const uint64_t* __restric
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
+// exclusive scan of the 256 bucket counts by ONE WARP (8 buckets per lane + a shuffle scan): this tiny kernel sits on
+// K_map's stream in front of every launch, where a single-thread loop cost 33 us (profiles/r2_launches_10M.csv)
 __global__ void len_scan_kernel(unsigned int* hist_then_cursor) {
-    unsigned int acc = 0;
-    for (uint32_t b = 0; b < kLenBuckets; ++b) {
-        const unsigned int c = hist_then_cursor[b];
-        hist_then_cursor[b] = acc;
-        acc += c;
+    const uint32_t lane = threadIdx.x;
+    unsigned int v[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[i] = hist_then_cursor[lane * 8 + i];
+        sum += v[i];
+    }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += up;
+    }
+    unsigned int acc = incl - sum;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        hist_then_cursor[lane * 8 + i] = acc;
+        acc += v[i];
     }
 }
 
@@ -458,7 +486,7 @@ cudaError_t launch_len_order(const uint64_t* offsets, const uint32_t* lens, uint
     if (err != cudaSuccess) return err;
     const unsigned hb = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
     len_hist_kernel<<<hb < 148u * 8u ? (hb ? hb : 1u) : 148u * 8u, 256, 0, s>>>(offsets, lens, n, blob_bytes, hist256);
-    len_scan_kernel<<<1, 1, 0, s>>>(hist256);
+    len_scan_kernel<<<1, 32, 0, s>>>(hist256);
     len_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(offsets, lens, n, blob_bytes, hist256, order);
     return cudaGetLastError();
 }

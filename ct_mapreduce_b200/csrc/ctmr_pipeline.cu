@@ -38,6 +38,9 @@ int ensure_stages(ctmr_ctx* c) {
         CU(c, cudaEventCreateWithFlags(&s.reduced, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&s.meta_done, cudaEventDisableTiming));
         CU(c, cudaMalloc(&s.blob, c->stage_bytes + 64));
+        // K_map stages records in 16-byte pieces, so its last copy may read up to 15 bytes past the slice's data (inside
+        // this allocation, never consumed): written once here so that those bytes are defined (compute-sanitizer initcheck)
+        CU(c, cudaMemsetAsync(s.blob, 0, c->stage_bytes + 64, s.stream));
         CU(c, cudaMalloc(&s.offsets, (E + 1) * sizeof(uint64_t)));
         CU(c, cudaMalloc(&s.issuer_idx, E * sizeof(uint32_t)));
         CU(c, cudaMalloc(&s.status, E));

@@ -544,3 +544,18 @@ def test_long_serials_are_declined_not_misdeduplicated(eng, ora):
         assert sum(counts.values()) == int(want.was_unknown[~long_].sum())
         if not flags:
             assert np.array_equal(got.sha256, want.sha256)
+
+
+def test_unmodelled_ctgo_cases_agree_between_oracle_and_gpu(eng, ora):
+    """The inputs of tests/test_ctgo_leniencies.py (where this path knowingly differs from Go's x509): whatever the oracle
+    says about them, both CUDA walkers say the same."""
+    from ct_mapreduce_b200 import capi
+    from test_ctgo_leniencies import CASES, cert
+    ders = [c[1] for c in CASES] * 2
+    blob, offs = pack(ders)
+    iblob, ioffs = pack([cert()])
+    idx = np.zeros(len(ders), np.uint32)
+    for flags in (0, capi.F_NO_FINGERPRINT):
+        r_gpu, r_ora, counts, odb, sc = run_both(eng, ora, blob, offs, iblob, ioffs, idx, flt=b"", log_expired=True, flags=flags)
+        assert_same(r_gpu, r_ora, sha=not flags)
+        assert np.array_equal(sc, odb.filter_counters())
