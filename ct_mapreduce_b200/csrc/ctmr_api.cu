@@ -130,7 +130,7 @@ void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o
         p.crldp_len = o->crldp_len;
     }
     {
-        static const int lp = env_int("CTMR_LIGHT_PREFETCH", 0);
+        static const int lp = env_int("CTMR_LIGHT_PREFETCH", 2);
         p.light_prefetch = (uint32_t)lp;
     }
     p.status_counts = c->st.status_counts;

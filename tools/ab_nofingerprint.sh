@@ -1,2 +1,9 @@
-P='import sys,json; d=json.loads(sys.stdin.readlines()[-1]); r=d["roofline"]; print("RESULT value %.1f M/s step %.2f ms map/step %.2f ms achieved %.0f GB/s frac %.3f" % (d["value"]/1e6, d["ms_per_step"], r["kernel_ms_per_step"], r["achieved"], r["frac"]))'
-for w in cfg2 cfg3 cfg5; do for v in "CTMR_MAP_LIGHT=0" "CTMR_MAP_LIGHT=1"; do echo "== $w $v"; env $v python bench.py --workload $w --no-fingerprint --steps 3 --warmup 2 --no-e2e --no-cpu-baseline 2>&1 | python -c "$P"; done; done
+#!/bin/bash
+# The reference-faithful path (no whole-certificate fingerprint): map_light_kernel with / without the record prefetch.
+# Usage (under gpurun): tools/ab_nofingerprint.sh [workload]
+W=${1:-cfg3}
+B="python bench.py --workload $W --no-fingerprint --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-secondary"
+P='import sys,json; d=json.loads(sys.stdin.readlines()[-1]); r=d["roofline"]; print("RESULT %7.1f Mentries/s  step_ms %7.3f  map_ms/step %7.3f  hbm_alg_GB/s %6.0f  hbm_frac %.4f" % (d["value"]/1e6, d["ms_per_step"], r["kernel_ms_per_step"], r["achieved"], r["frac"]))'
+for lp in 0 2 4 8 20 24; do
+  echo "== $W CTMR_LIGHT_PREFETCH=$lp"; CTMR_LIGHT_PREFETCH=$lp $B 2>/dev/null | python -c "$P" || CTMR_LIGHT_PREFETCH=$lp $B 2>&1 | tail -5
+done
