@@ -72,6 +72,8 @@ SharedLayout make_layout(uint64_t table_slots, uint64_t pair_slots, uint64_t met
     return l;
 }
 
+}  // namespace
+namespace ctmr_host {
 int ensure_scratch(ctmr_ctx* c, uint64_t n) {
     if (n <= c->scratch_cap) return CTMR_OK;
     CU(c, cudaDeviceSynchronize());
@@ -87,6 +89,8 @@ int ensure_scratch(ctmr_ctx* c, uint64_t n) {
     c->scratch_cap = n;
     return CTMR_OK;
 }
+}  // namespace ctmr_host
+namespace {
 
 }  // namespace
 
@@ -262,7 +266,6 @@ int peer_barrier(ctmr_ctx* c, uint32_t channel, cudaStream_t s) {
 }  // namespace ctmr_host
 
 namespace {
-int ensure_scratch(ctmr_ctx* c, uint64_t n);
 int reduce_on(ctmr_ctx* c, const ctmr_key* keys, uint64_t m, uint32_t* slot_of, uint32_t* pair_slot, uint8_t* was_unknown,
               uint8_t* first, cudaStream_t s, bool already_inserted = false) {
     if (!already_inserted) CU(c, launch_insert(c->st, keys, m, slot_of, s));
@@ -439,6 +442,10 @@ int ensure_frontend(ctmr_ctx* c) {
 
 }  // namespace
 
+namespace ctmr_host {
+int frontend_ensure(ctmr_ctx* c) { return ensure_frontend(c); }
+}  // namespace ctmr_host
+
 // =================================================================================================
 extern "C" {
 
@@ -552,6 +559,8 @@ void ctmr_destroy(ctmr_ctx* c) {
     }
     cudaFree(c->xchg); cudaFree(c->cursors); cudaFree(c->rev); cudaFree(c->in_slot); cudaFree(c->in_pair);
     for (cudaEvent_t e : c->ev_pulled)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_g)
         if (e) cudaEventDestroy(e);
     cudaFree(c->shared); cudaFree(c->small_dev);
     cudaFree(c->issuer_map_dev); cudaFree(c->keys_scratch); cudaFree(c->slot_scratch); cudaFree(c->pair_scratch);
@@ -1259,235 +1268,6 @@ int ctmr_evict_expired(ctmr_ctx* c, int64_t now_unix_sec, uint64_t* evicted_out)
     CU(c, launch_evict_reinsert(c->st, keep, counters[0], c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     cudaFree(keep);
-    return ctmr_check_device(c, nullptr);
-}
-
-// ------------------------------------------------------------------------------------------------ CT wire-format front end
-// get-entries strings -> decode -> framing -> Chain[0] identification -> the path.
-static int process_raw_impl(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out);
-
-int ctmr_process_raw(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {
-    const int rc = process_raw_impl(c, b, out);
-    if (rc != CTMR_OK && c && c->fe) {
-        // an upload of the NEXT chunk may still be reading the caller's text and an output copy may still be writing
-        // the caller's arrays: neither may outlive the call
-        const std::string keep = c->err;
-        cudaStreamSynchronize(c->fe->copy_stream);
-        cudaStreamSynchronize(c->stream);
-        c->err = keep;
-    }
-    return rc;
-}
-
-static int process_raw_impl(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) {
-    if (!c || !b || !out) return fail(c, CTMR_E_INVALID, "bad argument");
-    if (b->n && (!b->text || !b->leaf_input_off || !b->leaf_input_len || !b->extra_data_off || !b->extra_data_len))
-        return fail(c, CTMR_E_INVALID, "null batch buffers");
-    if (b->n == 0) return CTMR_OK;
-    CU(c, cudaSetDevice(c->device));
-    int rc = ensure_frontend(c);
-    if (rc) return rc;
-    FrontEnd* f = c->fe;
-    f->fe_ms = f->path_ms = 0.f;
-    f->launches = 0;
-    cudaStream_t s = c->stream;
-    const ctmr_out* po = &out->path;
-    const bool want_meta = po->first_issuer_dn || po->first_crldp || po->issuer_name_off || po->crldp_off;
-    const bool want_pem = po->pem != nullptr || po->pem_off != nullptr;
-    if (want_pem && !(po->pem && po->pem_off)) return fail(c, CTMR_E_INVALID, "pem and pem_off go together");
-    uint64_t pem_base = 0;
-    const uint64_t E = f->cap_entries;
-    // Two upload stages: while chunk k runs (and waits on its host round trips), chunk k+1's text and spans
-    // are already crossing PCIe on the copy stream.
-    struct Plan {
-        uint64_t lo = 0, hi = 0, text_bytes = 0;
-    };
-    auto upload = [&](uint64_t lo, int which, Plan& pl) -> int {
-        FeStage& st = f->stage[which];
-        // ---- chunk = as many entries as fit the entry and character budgets
-        uint64_t hi = lo, chars = 0, min_off = ~0ull, max_end = 0;
-        while (hi < b->n && hi - lo < E) {
-            const uint64_t l0 = b->leaf_input_off[hi], l1 = l0 + b->leaf_input_len[hi];
-            const uint64_t x0 = b->extra_data_off[hi], x1 = x0 + b->extra_data_len[hi];
-            if (l1 > b->text_bytes || x1 > b->text_bytes) return fail(c, CTMR_E_INVALID, "string span outside the text buffer");
-            const uint64_t add = (uint64_t)b->leaf_input_len[hi] + b->extra_data_len[hi];
-            if (chars + add > f->cap_text / 2) break;
-            chars += add;
-            min_off = std::min(min_off, std::min(l0, x0));
-            max_end = std::max(max_end, std::max(l1, x1));
-            ++hi;
-        }
-        if (hi == lo) return fail(c, CTMR_E_BATCH_TOO_LARGE, "a single entry exceeds the front end's character budget");
-        const uint64_t cnt = hi - lo;
-        pl.lo = lo;
-        pl.hi = hi;
-        CU(c, cudaStreamWaitEvent(f->copy_stream, st.consumed, 0));  // the decode that last read this stage has run
-        std::memcpy(st.h_leaf_len, b->leaf_input_len + lo, cnt * 4);
-        std::memcpy(st.h_extra_len, b->extra_data_len + lo, cnt * 4);
-        if (max_end - min_off <= f->cap_text) {  // strings in place inside the response bodies: one copy
-            pl.text_bytes = max_end - min_off;
-            for (uint64_t i = 0; i < cnt; ++i) {
-                st.h_leaf_off[i] = b->leaf_input_off[lo + i] - min_off;
-                st.h_extra_off[i] = b->extra_data_off[lo + i] - min_off;
-            }
-            CU(c, cudaMemcpyAsync(st.text + 16, b->text + min_off, pl.text_bytes, cudaMemcpyHostToDevice, f->copy_stream));
-        } else {  // scattered: pack on the host first
-            st.pack.resize(chars);
-            uint64_t w = 0;
-            for (uint64_t i = 0; i < cnt; ++i) {
-                st.h_leaf_off[i] = w;
-                std::memcpy(st.pack.data() + w, b->text + b->leaf_input_off[lo + i], b->leaf_input_len[lo + i]);
-                w += b->leaf_input_len[lo + i];
-                st.h_extra_off[i] = w;
-                std::memcpy(st.pack.data() + w, b->text + b->extra_data_off[lo + i], b->extra_data_len[lo + i]);
-                w += b->extra_data_len[lo + i];
-            }
-            pl.text_bytes = w;
-            CU(c, cudaMemcpyAsync(st.text + 16, st.pack.data(), pl.text_bytes, cudaMemcpyHostToDevice, f->copy_stream));
-        }
-        CU(c, cudaMemcpyAsync(st.leaf_off, st.h_leaf_off, cnt * 8, cudaMemcpyHostToDevice, f->copy_stream));
-        CU(c, cudaMemcpyAsync(st.extra_off, st.h_extra_off, cnt * 8, cudaMemcpyHostToDevice, f->copy_stream));
-        CU(c, cudaMemcpyAsync(st.leaf_len, st.h_leaf_len, cnt * 4, cudaMemcpyHostToDevice, f->copy_stream));
-        CU(c, cudaMemcpyAsync(st.extra_len, st.h_extra_len, cnt * 4, cudaMemcpyHostToDevice, f->copy_stream));
-        CU(c, cudaEventRecord(st.uploaded, f->copy_stream));
-        return CTMR_OK;
-    };
-    Plan plan[2];
-    rc = upload(0, 0, plan[0]);
-    if (rc) return rc;
-    for (int k = 0;; ++k) {
-        const Plan cur = plan[k & 1];
-        const uint64_t lo = cur.lo, hi = cur.hi, cnt = hi - lo;
-        if (hi < b->n) {  // next chunk's upload overlaps this chunk's kernels
-            rc = upload(hi, (k + 1) & 1, plan[(k + 1) & 1]);
-            if (rc) return rc;
-        }
-        FeStage& st = f->stage[k & 1];
-        CU(c, cudaStreamWaitEvent(s, st.uploaded, 0));
-        FeParams p{};
-        p.text = st.text + 16;
-        p.text_bytes = cur.text_bytes;
-        p.leaf_off = st.leaf_off; p.leaf_len = st.leaf_len; p.extra_off = st.extra_off; p.extra_len = st.extra_len;
-        p.n = cnt;
-        p.pad_size = f->pad_size; p.dec_off = f->dec_off; p.dec_len = f->dec_len; p.str_bad = f->str_bad; p.decoded = f->decoded;
-        p.entry_status = f->entry_status; p.entry_type = f->entry_type; p.timestamp = f->timestamp; p.leaf_src = f->leaf_src;
-        p.leaf_rel = f->leaf_rel; p.leaf_len_out = f->leaf_len_out; p.leaf_abs = f->leaf_abs; p.chain_abs = f->chain_abs;
-        p.chain_len = f->chain_len; p.tbs_abs = f->tbs_abs; p.tbs_len = f->tbs_len; p.issuer_idx = f->issuer_idx;
-        CU(c, cudaEventRecord(f->ev0, s));
-        CU(c, launch_fe_decode(p, f->scan_temp, f->scan_temp_bytes, c->sm_count, s));
-        CU(c, cudaEventRecord(st.consumed, s));  // text and spans are dead once decoded: the stage may be refilled
-        CU(c, launch_fe_frame(p, s));
-        f->launches += 5;  // sizes, scan (cub: one kernel visible to us), decode, frame, tbs
-        // ---- Chain[0] -> dense index; certificates never seen before go through ctmr_register_issuers once
-        for (int round = 0;; ++round) {
-            if (round > 64) return fail(c, CTMR_E_CUDA, "front end: issuer identification does not converge");
-            IssuerCertTable tab{f->slots_dev, f->slot_mask, f->arena};
-            CU(c, cudaMemsetAsync(f->pending, 0, (f->pending_mask + 1) * 8, s));
-            CU(c, cudaMemsetAsync(f->unknown_count, 0, 4, s));
-            CU(c, launch_fe_issuer(p, tab, f->pending, f->pending_mask, f->unknown_list, f->unknown_cap, f->unknown_count, c->sm_count, s));
-            ++f->launches;
-            unsigned int n_unknown = 0;
-            CU(c, cudaMemcpyAsync(&n_unknown, f->unknown_count, 4, cudaMemcpyDeviceToHost, s));
-            CU(c, cudaStreamSynchronize(s));
-            if (n_unknown == 0) break;
-            if (n_unknown > f->unknown_cap) n_unknown = f->unknown_cap;  // the rest shows up again next round
-            std::vector<uint32_t> list(n_unknown);
-            CU(c, cudaMemcpyAsync(list.data(), f->unknown_list, n_unknown * 4ull, cudaMemcpyDeviceToHost, s));
-            CU(c, cudaStreamSynchronize(s));
-            std::vector<uint8_t> blob;
-            std::vector<uint64_t> offs(1, 0);
-            for (uint32_t e : list) {
-                uint64_t at = 0;
-                uint32_t len = 0;
-                CU(c, cudaMemcpyAsync(&at, f->chain_abs + e, 8, cudaMemcpyDeviceToHost, s));
-                CU(c, cudaMemcpyAsync(&len, f->chain_len + e, 4, cudaMemcpyDeviceToHost, s));
-                CU(c, cudaStreamSynchronize(s));
-                const size_t w = blob.size();
-                blob.resize(w + len);
-                CU(c, cudaMemcpyAsync(blob.data() + w, f->decoded + at, len, cudaMemcpyDeviceToHost, s));
-                CU(c, cudaStreamSynchronize(s));
-                offs.push_back(blob.size());
-            }
-            std::vector<uint32_t> dense(n_unknown);
-            const uint64_t before = f->slots_used;
-            rc = ctmr_register_issuers(c, blob.data(), offs.data(), n_unknown, dense.data());
-            if (rc) return rc;
-            if (f->slots_used == before) return fail(c, CTMR_E_CUDA, "front end: unresolved Chain[0] is already registered");
-        }
-        CU(c, cudaEventRecord(f->ev1, s));
-        // ---- the path over the decoded arena: leaves stay where the decoder put them
-        ctmr_dev_batch db{};
-        db.blob = f->decoded;
-        CU(c, cudaMemcpyAsync(&db.blob_bytes, f->dec_off + 2 * cnt, 8, cudaMemcpyDeviceToHost, s));
-        CU(c, cudaStreamSynchronize(s));
-        db.offsets = f->leaf_abs;
-        db.lens = f->leaf_len_out;
-        db.n = cnt;
-        db.issuer_idx = f->issuer_idx;
-        db.first_index = c->next_index + lo;
-        db.now_unix_ns = b->now_unix_ns;
-        ctmr_dev_out dout{};
-        dout.status = f->status;
-        dout.sha256 = po->sha256 ? f->sha : nullptr;
-        dout.exp_hour = f->exp_hour;
-        dout.serial_off = f->serial_off;
-        dout.serial_len = f->serial_len;
-        dout.was_unknown = f->was_unknown;
-        dout.first_issuer_hour = f->first;
-        if (want_meta) {
-            dout.issuer_name_off = f->spans;
-            dout.issuer_name_len = f->spans + E;
-            dout.crldp_off = f->spans + 2 * E;
-            dout.crldp_len = f->spans + 3 * E;
-            dout.first_issuer_dn = f->first_meta;
-            dout.first_crldp = f->first_meta + E;
-        }
-        rc = ctmr_process_device(c, &db, &dout, s);
-        if (rc) return rc;
-        CU(c, launch_fe_finish(p, f->status, s));
-        ++f->launches;
-        CU(c, cudaEventRecord(f->ev2, s));
-        if (want_pem) {  // the decoded DER exists only on the device: its PEM is how new certificates reach the host
-            rc = pem_ensure(c, f->pem, E, f->cap_decoded);
-            if (rc) return rc;
-            rc = pem_chunk(c, f->pem, f->decoded, f->leaf_abs, f->leaf_len_out, f->was_unknown, cnt, po, lo, &pem_base, s);
-            if (rc) return rc;
-        }
-#define FE_D2H(dst, src, bytes) \
-    if (dst) CU(c, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(dst) + lo * ((bytes) / cnt), (src), (bytes), cudaMemcpyDeviceToHost, s))
-        FE_D2H(po->status, f->status, cnt);
-        FE_D2H(po->sha256, f->sha, cnt * 32);
-        FE_D2H(po->exp_hour, f->exp_hour, cnt * 8);
-        FE_D2H(po->serial_off, f->serial_off, cnt * 4);
-        FE_D2H(po->serial_len, f->serial_len, cnt * 4);
-        FE_D2H(po->was_unknown, f->was_unknown, cnt);
-        FE_D2H(po->first_issuer_hour, f->first, cnt);
-        if (want_meta) {
-            FE_D2H(po->issuer_name_off, dout.issuer_name_off, cnt * 4);
-            FE_D2H(po->issuer_name_len, dout.issuer_name_len, cnt * 4);
-            FE_D2H(po->crldp_off, dout.crldp_off, cnt * 4);
-            FE_D2H(po->crldp_len, dout.crldp_len, cnt * 4);
-            FE_D2H(po->first_issuer_dn, dout.first_issuer_dn, cnt);
-            FE_D2H(po->first_crldp, dout.first_crldp, cnt);
-        }
-        FE_D2H(out->entry_status, f->entry_status, cnt);
-        FE_D2H(out->entry_type, f->entry_type, cnt);
-        FE_D2H(out->timestamp_ms, f->timestamp, cnt * 8);
-        FE_D2H(out->issuer, f->issuer_idx, cnt * 4);
-        FE_D2H(out->leaf_src, f->leaf_src, cnt);
-        FE_D2H(out->leaf_off, f->leaf_rel, cnt * 4);
-        FE_D2H(out->leaf_len, f->leaf_len_out, cnt * 4);
-#undef FE_D2H
-        CU(c, cudaStreamSynchronize(s));
-        float a = 0.f, d = 0.f;
-        CU(c, cudaEventElapsedTime(&a, f->ev0, f->ev1));
-        CU(c, cudaEventElapsedTime(&d, f->ev1, f->ev2));
-        f->fe_ms += a;
-        f->path_ms += d;
-        if (hi >= b->n) break;
-    }
-    if (want_pem) po->pem_off[b->n] = pem_base;
-    c->next_index += b->n;
     return ctmr_check_device(c, nullptr);
 }
 

@@ -165,6 +165,7 @@ struct ctmr_ctx {
     unsigned long long* cursors = nullptr;  // [kParities][kMaxWorld] records appended per owner (local)
     uint32_t* rev = nullptr;                // [kParities][world][X] inbox position -> entry
     uint32_t *in_slot = nullptr, *in_pair = nullptr;  // [kParities][world][X] owner-side scratch of the inbox records
+    cudaEvent_t ev_g[3] = {};               // ctmr_group_process_raw: mapped / reduced / string identities inserted
     cudaEvent_t ev_pulled[kParities] = {};  // ctmr_process_device: round k's bits pulled (its exchange parity may be reused)
     unsigned long long epoch[kPeerChannels] = {};
     struct ctmr_group* group = nullptr;    // set when the ctx is a member of an in-process group
@@ -240,6 +241,8 @@ int upload_issuer_map(ctmr_ctx* c, const uint32_t* dense, uint32_t n);
 int preload_impl(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], const uint8_t* serial_blob, const uint64_t* serial_offsets,
                  uint64_t n, uint64_t first_index);
 int ensure_stages(ctmr_ctx* c);
+int frontend_ensure(ctmr_ctx* c);   // allocates the front end's buffers on first use (ctmr_api.cu)
+int ensure_scratch(ctmr_ctx* c, uint64_t n);
 uint32_t peer_rounds();   // rounds of the collective ctmr_process_device (CTMR_PEER_ROUNDS, env override for experiments)
 void pem_free(PemStage& ps);
 void stages_destroy(ctmr_ctx* c);

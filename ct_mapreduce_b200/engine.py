@@ -228,8 +228,11 @@ class GpuCertDatabase:
             _attach_pem(o.path, p, n, (int(leaf_len.sum()) + int(extra_len.sum())) // 4 * 3)
         b = capi.RawBatch(capi.ptr(text), text.size, capi.ptr(leaf_off), capi.ptr(leaf_len), capi.ptr(extra_off), capi.ptr(extra_len),
                           n, now_unix_ns)
-        self._check(self._lib.ctmr_process_raw(self._h, C.byref(b), C.byref(o)))
+        self._check(self._process_raw_fn()(self._h, C.byref(b), C.byref(o)))
         return r
+
+    def _process_raw_fn(self):
+        return self._lib.ctmr_process_raw
 
     def frontend_profile_last(self):
         """(frontend_ms, path_ms, frontend_launches) of the last store_raw_entries call (CUDA events inside the library)."""
@@ -380,6 +383,9 @@ class GpuCertGroup(GpuCertDatabase):
 
     def _process_batch_fn(self):
         return self._lib.ctmr_group_process_batch
+
+    def _process_raw_fn(self):
+        return self._lib.ctmr_group_process_raw
 
     def register_issuers(self, issuer_blob, issuer_offsets):
         return self.members[0].register_issuers(issuer_blob, issuer_offsets)   # the registry is the group's

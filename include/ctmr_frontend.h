@@ -82,6 +82,12 @@ typedef struct ctmr_raw_out {
  * following those of earlier ctmr_process_batch / ctmr_process_raw calls on this ctx. */
 int ctmr_process_raw(ctmr_ctx* ctx, const ctmr_raw_batch* batch, ctmr_raw_out* out);
 
+/* The same on every GPU of a group (ctmr_group_create, ctmr.h): each round takes one chunk per GPU out of ONE contiguous
+ * window of the batch, every GPU decodes and frames its chunk, Chain[0] certificates resolve against the group's issuer
+ * registry, and the path runs as one round of the group's key exchange -- entry i keeps global index next_index + i, so
+ * the outputs equal those of ctmr_process_raw on one GPU for the same pages. */
+int ctmr_group_process_raw(ctmr_group* g, const ctmr_raw_batch* batch, ctmr_raw_out* out);
+
 /* CUDA-event timings of the last ctmr_process_raw call: front-end kernels (decode, framing, issuer
  * identification) and the map/reduce that followed, summed over its chunks, in milliseconds */
 int ctmr_frontend_profile_last(ctmr_ctx* ctx, float* frontend_ms, float* path_ms, uint64_t* frontend_launches);

@@ -352,3 +352,39 @@ def test_peer_processes_match_sequential_oracle(ora, mode):
         for d, v in outs[r]["counts"].items():
             total[d] = (total.get(d, 0) + v) % (1 << 64)
     assert {k: v for k, v in total.items() if v} == odb.issuer_counts()
+
+
+@pytest.mark.parametrize("shards", ["one_gpu_three_shards", "all_gpus"])
+def test_group_front_end_matches_oracle(eng, ora, monkeypatch, shards):
+    """SURVEY §8(f)-2 on the group path (ctmr_group_process_raw): get-entries pages with every entry kind and malformation,
+    small staging budgets (many rounds, one chunk per shard each), several calls, string identities and PEM: every output
+    equals the oracle's sequential run over the same pages -- i.e. what ctmr_process_raw returns on one GPU."""
+    from conftest import go_pem
+    from test_gpu_frontend import check, synth_pages
+    sets = _device_sets()
+    if shards == "all_gpus" and len(sets) < 2:
+        pytest.skip("needs >= 2 GPUs")
+    devices = sets[0] if shards == "one_gpu_three_shards" else sets[1]
+    monkeypatch.setenv("CTMR_FE_TEXT_CAP", str(1 << 21))
+    n = 9000
+    text, lo, ll, xo, xl, _ = synth_pages(ora, n, seed=13, page=700, dup_mode=1)
+    odb = ora.DB(README_FILTER, False)
+    with eng.GpuCertGroup(devices, issuer_cn_filter=README_FILTER, table_capacity=1 << 16, max_batch_entries=600, max_issuers=1024) as g:
+        cuts = [0, 2500, 2501, n]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            check(eng, ora, g, odb, text, lo[a:b].copy(), ll[a:b].copy(), xo[a:b].copy(), xl[a:b].copy(), want_meta=True)
+        assert {k: v for k, v in g.issuer_counts().items() if v} == {k: v for k, v in odb.issuer_counts().items() if v}
+        assert np.array_equal(g.status_counters(), odb.filter_counters())
+        per = [m.table_stats()[0] for m in g.members]
+        assert all(p > 0 for p in per)
+        # a replay through the group: everything known; PEM only for new certificates (none)
+        r2 = g.store_raw_entries(text, lo, ll, xo, xl, NOW_NS, want_pem=True)
+        assert not r2.path.was_unknown.any() and int(r2.path.pem_off[-1]) == 0
+    # PEM of the new certificates, in entry order across the shards
+    odb2 = ora.DB(b"", True)
+    r_o = ora.raw_process(odb2, text, lo, ll, xo, xl, NOW_NS)
+    with eng.GpuCertGroup(devices, log_expired_entries=True, table_capacity=1 << 16, max_batch_entries=500) as g:
+        r_g = g.store_raw_entries(text, lo, ll, xo, xl, NOW_NS, want_pem=True)
+    assert np.array_equal(r_g.path.was_unknown, r_o.path.was_unknown)
+    for i in range(0, n, 7):
+        assert r_g.path.pem_of(i) == (go_pem(r_o.leaves[i]) if r_o.path.was_unknown[i] else b""), i
