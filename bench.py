@@ -281,6 +281,8 @@ def main():
             dist.init_process_group("gloo")
         else:
             dist.init_process_group("nccl", device_id=dev)
+    # a CPU-side barrier for the phase in which rank 0 alone drives every GPU (the one-process group form)
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
     cdev = torch.device("cpu") if same_gpu else dev   # where the bench's own (untimed) reductions live
     wname = default_workload(args, world)
     wl = WORKLOADS[wname]
@@ -618,9 +620,10 @@ def main():
                          args.secondary_entries or 100_000_000, capi.F_NO_FINGERPRINT))
         plan.append((f"configs[3] shape: {per_gpu * world / 1e6:.0f}M entries over {world} GPU(s)", "cfg4", per_gpu, 0))
         plan.append((f"configs[4] shape: {per_gpu * world / 1e6:.0f}M mixed-size entries, 50% duplicates, over {world} GPU(s)", "cfg5", per_gpu, 0))
-        def frontend_run(n_raw):
+        def frontend_run(n_raw, devices=None):
             """get-entries response bodies (JSON, base64 leaf_input / extra_data; 2/3 x509 entries, 1/3 precert
-            entries) through ctmr_process_raw: pinned host text in, host results out, every copy inside the timed calls."""
+            entries) through ctmr_process_raw -- or, with `devices`, through ctmr_group_process_raw on all of them from this one
+            process: pinned host text in, host results out, every copy inside the timed calls."""
             from ct_mapreduce_b200 import frontend  # noqa: F401  (span finder; the pages here come with their spans)
             cfgr = capi.synth_cfg(n_raw, seed=SEED + 2)
             need = lib.ctmr_synth_raw_pages_host(C.byref(cfgr), 0, n_raw, 1000, None, 0, None, None, None, None)
@@ -630,7 +633,10 @@ def main():
             assert lib.ctmr_synth_raw_pages_host(C.byref(cfgr), 0, n_raw, 1000, pin.addr, need, capi.ptr(lo_), capi.ptr(ll_), capi.ptr(xo_),
                                                  capi.ptr(xl_)) == need
             text = pin.view()
-            dbr = engine.GpuCertDatabase(device=local, log_expired_entries=True, table_capacity=pow2(4 * n_raw), max_issuers=4096)
+            if devices:
+                dbr = engine.GpuCertGroup(devices, log_expired_entries=True, table_capacity=pow2(4 * n_raw // len(devices)), max_issuers=4096)
+            else:
+                dbr = engine.GpuCertDatabase(device=local, log_expired_entries=True, table_capacity=pow2(4 * n_raw), max_issuers=4096)
             try:
                 fe_ms = path_ms = 0.0
                 reps = 3
@@ -639,7 +645,7 @@ def main():
                         ts_ = time.perf_counter()
                     r_ = dbr.store_raw_entries(text, lo_, ll_, xo_, xl_, NOW_NS)
                     if it >= 1:
-                        f_, p_, _ = dbr.frontend_profile_last()
+                        f_, p_, _ = (dbr.members[0] if devices else dbr).frontend_profile_last()
                         fe_ms += f_
                         path_ms += p_
                 dt_ = (time.perf_counter() - ts_) / reps
@@ -650,12 +656,14 @@ def main():
                 dbr.close()
                 pin.free()
             chars = int(ll_.sum()) + int(xl_.sum())
-            return {"name": "get-entries pages through ctmr_process_raw (CT wire-format front end, SURVEY 8(f)-2)", "entries": n_raw,
+            return {"name": ("get-entries pages through ctmr_group_process_raw on %d GPUs driven by one process (front end on the group path)" % len(devices))
+                            if devices else "get-entries pages through ctmr_process_raw (CT wire-format front end, SURVEY 8(f)-2)", "entries": n_raw,
                     "value": n_raw / dt_, "unit": "entries/s", "seconds": dt_, "text_bytes": int(need), "h2d_gbs": need / dt_ / 1e9,
                     "frontend_kernels_ms": fe_ms / reps, "frontend_kernels_entries_per_sec": n_raw / (fe_ms / reps) * 1e3,
                     "frontend_kernels_chars_gbs": chars / (fe_ms / reps) / 1e6, "path_ms": path_ms / reps,
                     "note": "whole calls: pinned host text in (PCIe bound: ~5 KB of base64 per entry), host results out; base64 decode, TLS "
-                            "framing, precert TBS check and Chain[0] identification on the GPU"}
+                            "framing, precert TBS check and Chain[0] identification on the GPU"
+                            + ("; kernel split = member 0's chunks; the text sits on rank 0's NUMA node" if devices else "")}
 
         for tag, wn, pe, fl in plan:
             try:
@@ -666,11 +674,21 @@ def main():
                     torch.cuda.synchronize(dev)
                 except Exception:
                     break
+        n_raw = min(600_000, max(20_000, (args.secondary_entries or 100_000_000) // 100))
         if world == 1:
             try:
-                secondary.append(frontend_run(min(600_000, max(20_000, (args.secondary_entries or 100_000_000) // 100))))
+                secondary.append(frontend_run(n_raw))
             except Exception as e:  # noqa: BLE001
                 secondary.append({"name": "ctmr_process_raw", "error": f"{type(e).__name__}: {e}"[:300]})
+        else:
+            # the front end on the multi-GPU path: the one-process group form, driven by rank 0 over every GPU of the job
+            # while the other ranks wait on a CPU barrier (their GPUs are idle: nothing of theirs is resident any more)
+            if rank == 0 and not same_gpu:
+                try:
+                    secondary.append(frontend_run(min(n_raw * world, 2_400_000), devices=list(range(world))))
+                except Exception as e:  # noqa: BLE001
+                    secondary.append({"name": "ctmr_group_process_raw", "error": f"{type(e).__name__}: {e}"[:300]})
+            dist.barrier(group=cpu_group)
 
     if rank == 0:
         roofline = {"bound": "int_alu" if not args.no_fingerprint else "hbm",

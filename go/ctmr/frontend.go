@@ -126,14 +126,11 @@ func (r *RawResult) Free() {
 }
 
 // ProcessRaw = GetRawEntries' base64 decode + ct.LogEntryFromLeaf + insertCTWorker + Store decisions for
-// every entry of the accumulated pages, in page order (single-GPU ctx).
+// every entry of the accumulated pages, in page order, on one GPU or on every GPU of the group.
 func (d *DB) ProcessRaw(p *RawPages, nowUnixNs int64, r *RawResult) error {
 	n := len(p.LeafOff)
 	if n == 0 {
 		return nil
-	}
-	if d.h == nil {
-		return fmt.Errorf("the wire-format front end runs on a single-GPU ctx")
 	}
 	b := (*C.ctmr_raw_batch)(C.calloc(1, C.size_t(unsafe.Sizeof(C.ctmr_raw_batch{}))))
 	defer C.free(unsafe.Pointer(b))
@@ -153,5 +150,8 @@ func (d *DB) ProcessRaw(p *RawPages, nowUnixNs int64, r *RawResult) error {
 	b.extra_data_len = (*C.uint32_t)(unsafe.Pointer(&p.ExtraLen[0]))
 	b.n = C.uint64_t(n)
 	b.now_unix_ns = C.int64_t(nowUnixNs)
+	if d.g != nil { // several GPUs: one chunk per GPU per round, the same outputs in entry order
+		return d.err(C.ctmr_group_process_raw(d.g, b, r.raw), "ctmr_group_process_raw")
+	}
 	return d.err(C.ctmr_process_raw(d.h, b, r.raw), "ctmr_process_raw")
 }
