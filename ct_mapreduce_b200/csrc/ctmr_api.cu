@@ -835,7 +835,9 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
     static const int map_streams = env_int("CTMR_MAP_STREAMS", 2);    // K_map launches alternate between two streams
     int nsub = coll ? (int)peer_rounds() : (b->n >= (1u << 21) ? 8 : (b->n >= (1u << 18) ? 2 : 1));
     if (!coll && rounds_env > 0 && b->n >= (1u << 18)) nsub = rounds_env > kMaxRounds ? kMaxRounds : rounds_env;
-    const uint64_t per_round = (b->n + nsub - 1) / nsub;
+    // Rounds of E entries with a SHORT last round (a quarter of E): what is exposed at the end of a call is the reduce chain
+    // of the last round, so that round is kept small; E stays uniform, which is all the global-index formula needs.
+    const uint64_t per_round = nsub >= 4 ? (4 * b->n + 4 * (uint64_t)nsub - 4) / (4 * (uint64_t)nsub - 3) : (b->n + nsub - 1) / nsub;
     if (coll && per_round > c->px.X)
         return fail(c, CTMR_E_BATCH_TOO_LARGE, "entries per round exceed the key-exchange regions: raise config.max_round_entries to ceil(n / ctmr_peer_rounds())");
     ctmr_key* keys = o->keys ? o->keys : c->keys_scratch;
@@ -847,13 +849,8 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
     CU(c, cudaStreamWaitEvent(c->stream_b, c->ev_fork, 0));
     for (int k = 0; k < nsub; ++k) {
         uint64_t lo, hi;
-        if (coll) {
-            lo = std::min<uint64_t>(b->n, per_round * k);
-            hi = std::min<uint64_t>(b->n, per_round * (k + 1));
-        } else {
-            lo = b->n * k / nsub;
-            hi = b->n * (k + 1) / nsub;
-        }
+        lo = std::min<uint64_t>(b->n, per_round * k);
+        hi = std::min<uint64_t>(b->n, per_round * (k + 1));
         const uint64_t cnt = hi - lo;
         ctmr_dev_batch sb = *b;
         sb.offsets = b->offsets + lo;

@@ -41,8 +41,10 @@ def attach_peers(db, group=None):
 
 
 def round_entries(n: int, rounds: int = 0) -> int:
-    """E of the collective ctmr_process_device: entries per rank and round (every rank passes the same n)."""
-    return -(-n // (rounds or capi.peer_rounds()))
+    """E of the collective ctmr_process_device: entries per rank and round (every rank passes the same n).  The last round
+    is a quarter of the others (its reduce chain is what a call exposes at its end): E = ceil(4n / (4R - 3)) for R >= 4."""
+    r = rounds or capi.peer_rounds()
+    return -(-4 * n // (4 * r - 3)) if r >= 4 else -(-n // r)
 
 
 def call_index_span(n: int, world: int, rounds: int = 0) -> int:

@@ -93,7 +93,7 @@ typedef struct ctmr_config {
     uint32_t flags;                  /* CTMR_F_* */
     uint32_t meta_capacity_log2;     /* IssuerMetadata string-identity table (issuer DN / CRL-DP bytes), log2 slots; 0 = 20, max 26 */
     uint64_t max_round_entries;      /* groups only: the most entries one GPU maps per round of ctmr_process_device
-                                      * (= ceil(n / CTMR_PEER_ROUNDS)); sizes the key-exchange regions (78 bytes x
+                                      * (= ceil(4n / (4R - 3)), R = ctmr_peer_rounds()); sizes the key-exchange regions (78 bytes x
                                       * GPUs x 3 per entry).  0 = the host pipeline's stage size (max_batch_entries) */
 } ctmr_config;
 
@@ -293,7 +293,9 @@ int ctmr_group_reset(ctmr_group* g);
  * ctmr_process_device, ctmr_process_batch, ctmr_reset_device and ctmr_peer_* are COLLECTIVE: every rank must make
  * the same sequence of calls.  Inside them the ranks meet at barriers kept in peer memory (no host round trip, no
  * NCCL on the data path); the global index of entry j of rank r's round k is first_index + (k * world + r) * E + j,
- * i.e. the result equals the sequential run over the rounds in rank order (E = entries per rank and round). */
+ * i.e. the result equals the sequential run over the rounds in rank order.  E = entries per rank and round: the host
+ * pipeline's stage size for ctmr_process_batch; for ctmr_process_device (every rank passes the same n, R =
+ * ctmr_peer_rounds() >= 4) E = ceil(4n / (4R - 3)), i.e. R - 1 full rounds and a last one a quarter as long. */
 #define CTMR_PEER_HANDLE_BYTES 256u
 /* allocates this rank's key-exchange area for a group of `world` ranks and exports it together with the tables */
 int ctmr_peer_export(ctmr_ctx* ctx, uint32_t world, uint8_t handle_out[CTMR_PEER_HANDLE_BYTES]);

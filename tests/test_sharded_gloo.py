@@ -216,15 +216,16 @@ def test_resolving_before_the_barrier_is_detectably_wrong(ora):
 
 def test_round_arithmetic():
     from ct_mapreduce_b200 import sharded
-    assert sharded.round_entries(10, 4) == 3 and sharded.round_entries(8, 4) == 2 and sharded.round_entries(1, 8) == 1
-    assert sharded.call_index_span(10, 3, 4) == 3 * 4 * 3
+    assert sharded.round_entries(10, 4) == 4 and sharded.round_entries(13, 4) == 4 and sharded.round_entries(1, 8) == 1
+    assert sharded.round_entries(10_000_000, 8) == 1_379_311 and sharded.round_entries(9, 2) == 5
+    assert sharded.call_index_span(10, 3, 4) == 3 * 4 * 4
     # every entry of every rank appears exactly once; rounds ascend, ranks ascend inside a round
     for n, world, rounds in ((10, 3, 4), (7, 2, 8), (64, 8, 8), (5, 1, 4)):
         seen = [np.zeros(n, int) for _ in range(world)]
         last = (-1, -1)
         e = sharded.round_entries(n, rounds)
         for r, lo, hi in sharded.sequential_order(n, world, rounds):
-            assert hi > lo and hi - lo <= e and lo % e == 0
+            assert hi > lo and hi - lo <= e and lo % e == 0 and (hi - lo == e or hi == n)
             k = lo // e
             assert (k, r) > last
             last = (k, r)
