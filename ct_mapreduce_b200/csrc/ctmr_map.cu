@@ -1,21 +1,19 @@
 // ctmr_map.cu -- the map half of the CT-entry hot path: hand-written sm_100a kernels.
 //
-// K_map      lane-per-certificate map: DER walk + certIsFilteredOut + SHA-256(leaf DER).
-//            Each lane streams ITS certificate through a private double-buffered shared-memory
-//            slot with per-lane TMA bulk copies (cp.async.bulk -> SASS UBLKCP) completing on a
-//            per-warp mbarrier pair, so global loads never occupy registers or the LSU while the
-//            INT pipe runs the 64-round compression.  (cmd/ct-fetch/ct-fetch.go:44-70,198-213,
-//            storage/types.go:171-178,339-346; fingerprint = crypto/sha256.Sum256(cert.Raw).)
-// K_insert   open-addressing find-or-insert of (exp_hour, issuer, raw serial) key records into the
-//            persistent known-certificate table; lowest global entry index wins via atomicMax on
-//            the complemented index (storage/knowncertificates.go:38-55 over SetInsert).
-// K_resolve  was_unknown = "I am the lowest index of my key"; per-issuer unique counts
-//            (Count()-sum semantics, cmd/storage-statistics/storage-statistics.go:44-53) with
-//            warp-aggregated atomics; (issuer, exp_hour) first-seen table insert.
-// K_pairs    first_issuer_hour bit (IssuerMetadata.Accumulate's seenExpDateBefore,
-//            storage/issuermetadata.go:95-108).
-// plus issuer preparation (SPKI SHA-256 = Issuer.ID digest, storage/types.go:124-130,155-159),
-// set-cardinality scan, and the multi-GPU key partition / bit scatter helpers.
+// K_map        (map_stream_kernel<8,128,0,1>) lane-per-certificate map: DER walk + certIsFilteredOut + SHA-256(leaf DER).
+//              Each lane streams ITS certificate through a private double-buffered shared-memory window filled by
+//              asynchronous 16-byte global->shared copies (cp.async.cg -> SASS LDGSTS, per-thread commit / wait groups: no
+//              barrier is shared between lanes), so certificate bytes never occupy registers while the INT pipe runs the
+//              64-round compression; the resumable walker (ctmr_stream.cuh) eats from the same window.  Epilogue: filter,
+//              outputs, key record, and the key's route -- fused find-or-insert into this GPU's table when it owns the set,
+//              else an append to the owner GPU's inbox over NVLink (route_append).
+//              (cmd/ct-fetch/ct-fetch.go:44-70,198-213, storage/types.go:171-178,339-346; fingerprint =
+//              crypto/sha256.Sum256(cert.Raw).)  The TMA bulk-copy loader (LOADER = 1) is an experiment, see DESIGN.md.
+// K_map_light  (map_light_kernel) the same outputs without the fingerprint: thread per certificate, loads through L1.
+// length bucketing (len_hist / len_scan / len_scatter): processing order with equally long records per warp.
+// sha_ceiling_kernel: the register-only SHA-256 microbenchmark the roofline is quoted against.
+// The reduce half (K_insert / K_resolve / K_pairs, string identities, the owner and source passes of the multi-GPU key
+// exchange, the issuer registry, the peer barrier) lives in ctmr_reduce.cu.
 #include "ctmr_common.cuh"
 #include "ctmr_stream.cuh"
 
