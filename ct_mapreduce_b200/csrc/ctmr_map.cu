@@ -51,7 +51,9 @@ __device__ __forceinline__ void route_append(const RouteOut& r, bool remote, uin
 // through L1 (the full 256 KB is available as cache), 32 resident warps per SM to hide the pointer
 // chase.  The streaming kernel, which must stage every byte, tops out at ~2.0 TB/s here.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 4) map_light_kernel(const __grid_constant__ MapParams p) {
+// 6 resident CTAs per SM (40 registers, 60 bytes of spills): +9 % over 4 CTAs (56 registers), 8 CTAs (32 registers) spill too much
+// (profiles/r2_ab_light_occupancy.log)
+__global__ void __launch_bounds__(256, 6) map_light_kernel(const __grid_constant__ MapParams p) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = e < p.n;
     uint32_t status = CTMR_ST_PARSE_ERR;
