@@ -438,6 +438,14 @@ class GpuCertGroup(GpuCertDatabase):
         self._check(self._lib.ctmr_group_table_stats(self._h, C.byref(used), C.byref(cap)))
         return used.value, cap.value
 
+    def _single_ctx_only(self, *a, **k):
+        raise CtmrError(capi.E_INVALID, "this entry point takes one ctx: use group.members[r] (read side) or the group's own methods")
+
+    # the device-resident / per-ctx entry points of the base class do not take a group handle
+    map_device = reduce_device = process_device = read_histogram_device = profile_last = sha256_ceiling = _single_ctx_only
+    reset_device = check_device = peer_export = peer_attach = peer_barrier_device = _single_ctx_only
+    peer_allreduce_histogram_device = snapshot = restore = frontend_profile_last = _single_ctx_only
+
 
 # ---------------------------------------------------------------------- synthetic corpus (bench/test tooling)
 def synth_issuers(cfg: capi.SynthCfg):
