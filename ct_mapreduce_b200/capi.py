@@ -38,7 +38,7 @@ EXPORTS = [
     "ctmr_group_process_batch", "ctmr_group_issuer_counts", "ctmr_group_set_cardinality", "ctmr_group_status_counters",
     "ctmr_group_table_stats", "ctmr_group_preload_known", "ctmr_group_evict_expired", "ctmr_group_reset",
     "ctmr_peer_export", "ctmr_peer_attach", "ctmr_peer_barrier_device", "ctmr_peer_allreduce_histogram_device",
-    "ctmr_bind_host_to_device", "ctmr_peer_rounds",
+    "ctmr_bind_host_to_device", "ctmr_peer_rounds", "ctmr_peer_round_entries",
 ]
 PEER_HANDLE_BYTES = 256
 PEER_ROUNDS = 8   # default; peer_rounds() asks the library (environment override)
@@ -190,6 +190,8 @@ def load():
     L.ctmr_peer_allreduce_histogram_device.argtypes = [vp, vp, u32, vp, vp]
     L.ctmr_bind_host_to_device.argtypes = [C.c_int32]
     L.ctmr_peer_rounds.restype = u32
+    L.ctmr_peer_round_entries.argtypes = [u64]
+    L.ctmr_peer_round_entries.restype = u64
     for name in EXPORTS:
         getattr(L, name)  # every symbol include/ctmr.h declares must resolve
     _lib = L

@@ -253,6 +253,13 @@ int round_pull(ctmr_ctx* c, int parity, uint64_t maxr, uint8_t* was_unknown, uin
     return CTMR_OK;
 }
 
+// Rounds of E entries with a SHORT last round (a quarter of E): what a call exposes at its end is the reduce chain of its
+// last round, so that round is kept small; E stays uniform, which is all the global-index formula needs.
+uint64_t device_round_entries(uint64_t n, uint32_t rounds) {
+    if (rounds >= 4) return (4 * n + 4 * (uint64_t)rounds - 4) / (4 * (uint64_t)rounds - 3);
+    return rounds ? (n + rounds - 1) / rounds : n;
+}
+
 uint32_t peer_rounds() {
     static const int r = env_int("CTMR_PEER_ROUNDS", (int)CTMR_PEER_ROUNDS);
     return (uint32_t)(r < 1 ? 1 : (r > kMaxRounds ? kMaxRounds : r));
@@ -835,9 +842,7 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
     static const int map_streams = env_int("CTMR_MAP_STREAMS", 2);    // K_map launches alternate between two streams
     int nsub = coll ? (int)peer_rounds() : (b->n >= (1u << 21) ? 8 : (b->n >= (1u << 18) ? 2 : 1));
     if (!coll && rounds_env > 0 && b->n >= (1u << 18)) nsub = rounds_env > kMaxRounds ? kMaxRounds : rounds_env;
-    // Rounds of E entries with a SHORT last round (a quarter of E): what is exposed at the end of a call is the reduce chain
-    // of the last round, so that round is kept small; E stays uniform, which is all the global-index formula needs.
-    const uint64_t per_round = nsub >= 4 ? (4 * b->n + 4 * (uint64_t)nsub - 4) / (4 * (uint64_t)nsub - 3) : (b->n + nsub - 1) / nsub;
+    const uint64_t per_round = device_round_entries(b->n, (uint32_t)nsub);
     if (coll && per_round > c->px.X)
         return fail(c, CTMR_E_BATCH_TOO_LARGE, "entries per round exceed the key-exchange regions: raise config.max_round_entries to ceil(n / ctmr_peer_rounds())");
     ctmr_key* keys = o->keys ? o->keys : c->keys_scratch;
@@ -929,6 +934,7 @@ int ctmr_process_device(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out
 /* CUDA-event timings of the last ctmr_process_device call (after the caller synchronised):
  * map_ms = sum of the K_map stage durations on their stream, total_ms = first map start -> last reduce end */
 uint32_t ctmr_peer_rounds(void) { return peer_rounds(); }
+uint64_t ctmr_peer_round_entries(uint64_t n) { return device_round_entries(n, peer_rounds()); }
 
 int ctmr_profile_last(ctmr_ctx* c, float* map_ms, float* total_ms) {
     if (!c || c->last_sub <= 0) return fail(c, CTMR_E_INVALID, "no ctmr_process_device call to report");

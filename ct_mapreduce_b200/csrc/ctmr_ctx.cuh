@@ -161,6 +161,7 @@ struct ctmr_ctx {
     // key exchange of a group: peer-visible area (inboxes, result bits, region sizes) + private bookkeeping
     uint8_t* xchg = nullptr;
     uint64_t X = 0, cfg_round_entries = 0;
+    uint32_t exported_world = 0;            // ctmr_peer_export was called for a group of this size (the views follow at attach)
     PeerExchange px{};
     unsigned long long* cursors = nullptr;  // [kParities][kMaxWorld] records appended per owner (local)
     uint32_t* rev = nullptr;                // [kParities][world][X] inbox position -> entry
@@ -243,6 +244,7 @@ int preload_impl(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], const 
 int ensure_stages(ctmr_ctx* c);
 int frontend_ensure(ctmr_ctx* c);   // allocates the front end's buffers on first use (ctmr_api.cu)
 int ensure_scratch(ctmr_ctx* c, uint64_t n);
+uint64_t device_round_entries(uint64_t n, uint32_t rounds);   // E of a ctmr_process_device call cut into `rounds` rounds
 uint32_t peer_rounds();   // rounds of the collective ctmr_process_device (CTMR_PEER_ROUNDS, env override for experiments)
 void pem_free(PemStage& ps);
 void stages_destroy(ctmr_ctx* c);

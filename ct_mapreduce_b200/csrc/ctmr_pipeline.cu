@@ -654,10 +654,10 @@ int ctmr_peer_export(ctmr_ctx* c, uint32_t world, uint8_t handle_out[CTMR_PEER_H
     cudaError_t e = cudaIpcGetMemHandle(&h.mem, c->shared);
     if (e != cudaSuccess) return fail(c, CTMR_E_PEER, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
     if (world > 1) {
-        if (c->xchg && c->px.world != world) return fail(c, CTMR_E_INVALID, "already exported for a different group size");
+        if (c->xchg && c->exported_world != world) return fail(c, CTMR_E_INVALID, "already exported for a different group size");
         const int rc = alloc_exchange(c, world);
         if (rc) return rc;
-        c->px.world = world;  // remembered for the check above; the views are set by ctmr_peer_attach
+        c->exported_world = world;  // the views of the peers' areas are set by ctmr_peer_attach
         e = cudaIpcGetMemHandle(&h.xchg, c->xchg);
         if (e != cudaSuccess) return fail(c, CTMR_E_PEER, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
     }
@@ -678,7 +678,7 @@ int ctmr_peer_attach(ctmr_ctx* c, uint32_t rank, uint32_t world, const uint8_t* 
     if (c->peer_mode != PEER_NONE || c->group) return fail(c, CTMR_E_INVALID, "ctx already belongs to a group");
     CU(c, cudaSetDevice(c->device));
     if (world == 1) return CTMR_OK;
-    if (!c->xchg) return fail(c, CTMR_E_INVALID, "call ctmr_peer_export(ctx, world, ...) first");
+    if (!c->xchg || c->exported_world != world) return fail(c, CTMR_E_INVALID, "call ctmr_peer_export(ctx, world, ...) with this group size first");
     uint8_t *bases[kMaxWorld] = {}, *xb[kMaxWorld] = {};
     auto close_all = [&]() {
         for (uint32_t q = 0; q < kMaxWorld; ++q) {

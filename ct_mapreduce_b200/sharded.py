@@ -43,8 +43,9 @@ def attach_peers(db, group=None):
 def round_entries(n: int, rounds: int = 0) -> int:
     """E of the collective ctmr_process_device: entries per rank and round (every rank passes the same n).  The last round
     is a quarter of the others (its reduce chain is what a call exposes at its end): E = ceil(4n / (4R - 3)) for R >= 4."""
-    r = rounds or capi.peer_rounds()
-    return -(-4 * n // (4 * r - 3)) if r >= 4 else -(-n // r)
+    if not rounds:
+        return int(capi.load().ctmr_peer_round_entries(n))   # the library's own answer (its round count may be overridden)
+    return -(-4 * n // (4 * rounds - 3)) if rounds >= 4 else -(-n // rounds)
 
 
 def call_index_span(n: int, world: int, rounds: int = 0) -> int:

@@ -309,6 +309,9 @@ int ctmr_peer_allreduce_histogram_device(ctmr_ctx* ctx, uint64_t* counts_dst, ui
  * variable of the same name overrides it for experiments; identical on every rank) */
 #define CTMR_PEER_ROUNDS 8u
 uint32_t ctmr_peer_rounds(void);
+/* E of a collective ctmr_process_device call over n entries per rank: what config.max_round_entries must cover and what
+ * the global-index formula above uses (R - 1 rounds of E entries and a short last one) */
+uint64_t ctmr_peer_round_entries(uint64_t n);
 
 /* ---- host placement -------------------------------------------------------------------------------- */
 /* Binds the calling thread to the CPUs of the NUMA node `device` hangs off (sysfs), so that pinned buffers it

@@ -219,6 +219,9 @@ def test_round_arithmetic():
     assert sharded.round_entries(10, 4) == 4 and sharded.round_entries(13, 4) == 4 and sharded.round_entries(1, 8) == 1
     assert sharded.round_entries(10_000_000, 8) == 1_379_311 and sharded.round_entries(9, 2) == 5
     assert sharded.call_index_span(10, 3, 4) == 3 * 4 * 4
+    from ct_mapreduce_b200 import capi   # the Python restatement and the library agree (no GPU needed for this entry point)
+    for n in (1, 7, 4096, 10_000_000, 125_000_001):
+        assert sharded.round_entries(n) == sharded.round_entries(n, capi.peer_rounds())
     # every entry of every rank appears exactly once; rounds ascend, ranks ascend inside a round
     for n, world, rounds in ((10, 3, 4), (7, 2, 8), (64, 8, 8), (5, 1, 4)):
         seen = [np.zeros(n, int) for _ in range(world)]
