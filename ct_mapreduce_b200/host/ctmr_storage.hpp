@@ -501,6 +501,10 @@ struct BatchStats {
 class GpuCertDatabase {
   public:
     GpuCertDatabase(ctmr_ctx* ctx, RemoteCache* cache, StorageBackend* backend) : ctx_(ctx), cache_(cache), backend_(backend) {}
+    // several GPUs behind one handle (ctmr_group_*): the same StoreBatch, the fan-out is inside the library; registry
+    // questions (issuer digests) go to member 0, whose registry is the group's
+    GpuCertDatabase(ctmr_group* group, RemoteCache* cache, StorageBackend* backend)
+        : ctx_(ctmr_group_member(group, 0)), group_(group), cache_(cache), backend_(backend) {}
 
     // filesystemdatabase.go:213-240 / :40-57 -- objects are created on demand and kept for the process lifetime
     KnownCertificates* GetKnownCertificates(const ExpDate& e, const Issuer& i) {
@@ -532,8 +536,10 @@ class GpuCertDatabase {
         ctmr_out out{status.data(), nullptr, exp_hour.data(), soff.data(), slen.data(), unknown.data(), first.data(),
                      noff.data(), nlen.data(), coff.data(), clen.data(), first_dn.data(), first_crl.data(),
                      pem.data(), pem.size(), pem_off.data()};
-        int rc = ctmr_process_batch(ctx_, blob, offsets, n, issuer_blob, issuer_offsets, n_issuers, issuer_idx, now_unix_ns, &out);
-        if (rc != CTMR_OK) return std::string("ctmr_process_batch: ") + ctmr_last_error(ctx_);  // like a Redis outage: the caller stops
+        int rc = group_ ? ctmr_group_process_batch(group_, blob, offsets, n, issuer_blob, issuer_offsets, n_issuers, issuer_idx, now_unix_ns, &out)
+                        : ctmr_process_batch(ctx_, blob, offsets, n, issuer_blob, issuer_offsets, n_issuers, issuer_idx, now_unix_ns, &out);
+        if (rc != CTMR_OK)  // like a Redis outage: the caller stops
+            return std::string("ctmr_process_batch: ") + (group_ ? ctmr_group_last_error(group_) : ctmr_last_error(ctx_));
         std::vector<uint32_t> dense(n_issuers);
         if (n_issuers) {
             rc = ctmr_register_issuers(ctx_, issuer_blob, issuer_offsets, n_issuers, dense.data());  // memoised: no GPU work
@@ -624,6 +630,7 @@ class GpuCertDatabase {
 
   private:
     ctmr_ctx* ctx_;
+    ctmr_group* group_ = nullptr;
     RemoteCache* cache_;
     StorageBackend* backend_;
     std::map<std::string, std::unique_ptr<KnownCertificates>> known_;

@@ -122,7 +122,7 @@ static std::string hex(const std::string& s) {
     return o;
 }
 
-static int run_gpu(const std::string& dir, int batches, bool pipelined) {
+static int run_gpu(const std::string& dir, int batches, bool pipelined, int shards) {
     auto blob = read_all<uint8_t>(dir + "/blob.bin");
     auto offs = read_all<uint64_t>(dir + "/offsets.bin");
     auto iblob = read_all<uint8_t>(dir + "/issuer_blob.bin");
@@ -137,12 +137,24 @@ static int run_gpu(const std::string& dir, int batches, bool pipelined) {
     cfg.issuer_cn_filter = filt.data();
     cfg.issuer_cn_filter_len = (uint32_t)filt.size();
     ctmr_ctx* ctx = nullptr;
-    if (ctmr_create(&cfg, &ctx) != CTMR_OK) { std::fprintf(stderr, "ctmr_create: %s\n", ctmr_last_error(nullptr)); return 3; }
+    ctmr_group* group = nullptr;
+    if (shards > 1) {  // several shards on device 0: the group API from C++ (what the Go host calls on a multi-GPU box)
+        cfg.max_batch_entries = 512;  // many rounds per batch
+        std::vector<int32_t> devs((size_t)shards, 0);
+        if (ctmr_group_create(&cfg, devs.data(), (uint32_t)shards, &group) != CTMR_OK) {
+            std::fprintf(stderr, "ctmr_group_create: %s\n", ctmr_group_last_error(nullptr));
+            return 3;
+        }
+    } else if (ctmr_create(&cfg, &ctx) != CTMR_OK) {
+        std::fprintf(stderr, "ctmr_create: %s\n", ctmr_last_error(nullptr));
+        return 3;
+    }
     MockBatchRemoteCache batch_cache;  // offers SetInsertBatch / ExpireAtBatch (found by dynamic_cast in StoreBatch)
     MockRemoteCache plain_cache;
     MockRemoteCache& cache = pipelined ? static_cast<MockRemoteCache&>(batch_cache) : plain_cache;
     MockBackend backend;
-    GpuCertDatabase db(ctx, &cache, &backend);
+    GpuCertDatabase db_single(ctx, &cache, &backend), db_group(group, &cache, &backend);
+    GpuCertDatabase& db = group ? db_group : db_single;
     BatchStats total{};
     for (int b = 0; b < batches; ++b) {
         const uint64_t lo = n * b / batches, hi = n * (b + 1) / batches;
@@ -183,7 +195,8 @@ static int run_gpu(const std::string& dir, int batches, bool pipelined) {
         if (kv.first.compare(0, 9, "serials::") != 0) continue;
         out << "COUNT " << kv.first << " " << kv.second.size() << "\n";
     }
-    ctmr_destroy(ctx);
+    if (group) ctmr_group_destroy(group);
+    else ctmr_destroy(ctx);
     return 0;
 }
 
@@ -218,7 +231,8 @@ int main(int argc, char** argv) {
         return 0;
     }
     if (argc >= 4 && std::string(argv[1]) == "gpu")
-        return run_gpu(argv[2], std::atoi(argv[3]), argc >= 5 && std::string(argv[4]) == "pipelined");
+        return run_gpu(argv[2], std::atoi(argv[3]), argc >= 5 && std::string(argv[4]) == "pipelined",
+                       argc >= 6 ? std::atoi(argv[5]) : (argc >= 5 && std::string(argv[4]) == "group" ? 3 : 1));
     std::fprintf(stderr, "usage: host_tests cpu | gpu <dir> <batches>\n");
     return 64;
 }

@@ -33,7 +33,7 @@ def test_reference_reducer_tests_on_cpp_host(host_bin):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["per_entry", "pipelined"])
+@pytest.mark.parametrize("mode", ["per_entry", "pipelined", "group_of_three_shards"])
 def test_store_batch_drives_remote_cache_like_the_reference(host_bin, ora, tmp_path, mode):
     n = 6000
     cfg = ora.synth_cfg(n, len_mode=1, len_lo=512, len_hi=4096, dup_mode=1)
@@ -46,7 +46,9 @@ def test_store_batch_drives_remote_cache_like_the_reference(host_bin, ora, tmp_p
         np.ascontiguousarray(arr).tofile(tmp_path / f"{name}.bin")
     # "pipelined": the cache also implements BatchRemoteCache (SetInsertBatch / ExpireAtBatch): same final state,
     # but the serial inserts and expiries of a batch travel in one round trip each
-    r = subprocess.run([host_bin, "gpu", str(tmp_path), "3"] + (["pipelined"] if mode == "pipelined" else []), capture_output=True, text=True)
+    # "group_of_three_shards": the same StoreBatch over ctmr_group_* (three shards on device 0, 512-entry rounds)
+    extra = {"per_entry": [], "pipelined": ["pipelined"], "group_of_three_shards": ["group"]}[mode]
+    r = subprocess.run([host_bin, "gpu", str(tmp_path), "3"] + extra, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
 
     # what the reference would have left behind (sequential Store semantics from the oracle)
