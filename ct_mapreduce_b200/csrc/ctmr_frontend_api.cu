@@ -13,6 +13,8 @@
 //   back     x509 leaf failures, PEM of the new certificates, outputs to the host.
 // On a group a round takes one chunk per member, cut from ONE contiguous window of the batch, so that entry i keeps
 // global index next_index + i and the result equals the single-GPU / sequential run on the same pages.
+#include <thread>
+
 #include "ctmr_ctx.cuh"
 
 namespace {
@@ -301,6 +303,21 @@ int process_raw_single(ctmr_ctx* c, const ctmr_raw_batch* b, ctmr_raw_out* out) 
     return ctmr_check_device(c, nullptr);
 }
 
+// fn(r) for every member, on one thread each (the halves of a chunk wait on the host: issuer round trips, D2H); sequential if
+// threads cannot be had.  No exception leaves this function (C ABI).
+template <class F>
+void for_each_member(uint32_t W, std::vector<int>& rcs, F fn) {
+    rcs.assign(W, CTMR_OK);
+    std::vector<std::thread> th;
+    uint32_t started = 0;
+    try {
+        for (; started < W; ++started) th.emplace_back([&rcs, &fn, r = started] { rcs[r] = fn(r); });
+    } catch (...) {
+    }
+    for (std::thread& t : th) t.join();
+    for (uint32_t r = started; r < W; ++r) rcs[r] = fn(r);
+}
+
 // One round of the path over the members' device-resident chunks: map + route, [events], owner passes, [events], pull,
 // [string identities: insert, events, read-back].  Each member works on its own stream; rounds are serialised by the
 // callers' fe_back, which is also what orders the rounds for lowest-index-wins.
@@ -456,17 +473,31 @@ int process_raw_group(ctmr_group* g, const ctmr_raw_batch* b, ctmr_raw_out* out,
             rc = plan_round(g, b, end, (k + 1) & 1, nxt, failed);
             if (rc) return rc;
         }
-        for (uint32_t r = 0; r < W; ++r) {
-            *failed = g->m[r];
-            rc = fe_front(g->m[r], b, out, cur[r], g->next_index + cur[r].lo);
-            if (rc) return rc;
-        }
+        // The front halves wait on the host (issuer identification round trips, the arena size): one thread per member, so
+        // that the members' waits overlap instead of adding up.  Each thread touches its own ctx only; the issuer registry
+        // they all resolve against is device memory reached with atomics.
+        std::vector<int> rcs;
+        for_each_member(W, rcs, [&](uint32_t r) { return fe_front(g->m[r], b, out, cur[r], g->next_index + cur[r].lo); });
+        for (uint32_t r = 0; r < W; ++r)
+            if (rcs[r]) {
+                *failed = g->m[r];
+                return rcs[r];
+            }
         rc = group_round(g, cur.data(), k % (int)kParities, failed);
         if (rc) return rc;
-        for (uint32_t r = 0; r < W; ++r) {  // in entry order: the PEM texts are appended in that order
-            *failed = g->m[r];
-            rc = fe_back(g->m[r], out, cur[r], &pem_base);
-            if (rc) return rc;
+        if (out->path.pem) {
+            for (uint32_t r = 0; r < W; ++r) {  // in entry order: the PEM texts are appended in that order
+                *failed = g->m[r];
+                rc = fe_back(g->m[r], out, cur[r], &pem_base);
+                if (rc) return rc;
+            }
+        } else {  // disjoint output ranges: the members' copies and waits overlap as well
+            for_each_member(W, rcs, [&](uint32_t r) { return fe_back(g->m[r], out, cur[r], &pem_base); });
+            for (uint32_t r = 0; r < W; ++r)
+                if (rcs[r]) {
+                    *failed = g->m[r];
+                    return rcs[r];
+                }
         }
         pos = end;
         if (end >= b->n) break;
