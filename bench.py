@@ -688,6 +688,7 @@ def main():
                     secondary.append(frontend_run(min(n_raw * world, 2_400_000), devices=list(range(world))))
                 except Exception as e:  # noqa: BLE001
                     secondary.append({"name": "ctmr_group_process_raw", "error": f"{type(e).__name__}: {e}"[:300]})
+                torch.cuda.set_device(local)   # the group's calls left another device current on this thread
             dist.barrier(group=cpu_group)
 
     if rank == 0:
@@ -731,8 +732,11 @@ def main():
             line["secondary"] = secondary
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        try:  # the line is out: nothing below may keep the job from ending
+            dist.barrier(group=cpu_group)
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
     return 0
 
 
