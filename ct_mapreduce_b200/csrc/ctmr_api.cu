@@ -89,12 +89,7 @@ int ensure_scratch(ctmr_ctx* c, uint64_t n) {
     c->scratch_cap = n;
     return CTMR_OK;
 }
-}  // namespace ctmr_host
-namespace {
 
-}  // namespace
-
-namespace ctmr_host {
 void fill_map_params(ctmr_ctx* c, const ctmr_dev_batch* b, const ctmr_dev_out* o, MapParams& p, int counter_slot,
                      uint32_t* fused_slot_of, int parity) {
     std::memset(&p, 0, sizeof p);

@@ -1,3 +1,6 @@
+# needs the experiments build (the product library carries one instantiation of the streaming kernel)
+export CTMR_EXPERIMENTS=1
+python -m ct_mapreduce_b200.build --force > /dev/null || exit 1
 # K_map alone (4 M x 1.5 KB, map_device only) at different residency shapes; see DESIGN.md "Measured and rejected"
 for v in "CTMR_MAP_CHUNK=128" "CTMR_MAP_CHUNK=64" "CTMR_MAP_CHUNK=128 CTMR_MAP_WARPS=6"; do echo "== $v"; env $v CTMR_FUSE_INSERT=0 python - <<'PY' 2>&1 | tail -1
 import os, sys
