@@ -106,6 +106,17 @@ def test_no_cpu_fallback_without_gpu(lib):
     assert ei.value.code == capi.E_NO_DEVICE
 
 
+def test_group_has_no_cpu_fallback_either(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ct_mapreduce_b200 import capi, engine
+    with pytest.raises(capi.CtmrError) as ei:
+        engine.GpuCertGroup([0, 0])
+    assert ei.value.code == capi.E_NO_DEVICE
+    assert lib.ctmr_peer_rounds() == capi.PEER_ROUNDS and lib.ctmr_peer_round_entries(10_000_000) == 1_379_311
+
+
 def test_product_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under ct_mapreduce_b200/ or include/ may reference it."""
     bad = []
