@@ -120,3 +120,51 @@ def test_mixed_sizes_50pct_duplicates_4M():
     assert torch.equal(wu[ok].bool(), first_of_pair)
     assert sum(db.issuer_counts().values()) == int(wu.sum())
     db.close()
+
+
+@pytest.mark.timeout(600)
+def test_group_host_call_1M_entries_with_duplicates():
+    """The Go-facing multi-GPU entry point at a batch size that takes dozens of rounds: 1 M entries (every certificate
+    twice) through ctmr_group_process_batch on every GPU of the box -- or, on a 1-GPU box, on two shards of cuda:0 --
+    checked by properties: exactly the EARLIER twin of every kept pair is unknown (twins mostly live on different shards and
+    in different rounds), the summed histogram equals the bits, a replay finds everything known, and the group's answers
+    equal a single GPU's on the same batch."""
+    import torch
+    from ct_mapreduce_b200 import capi, engine
+    n = 1_000_000
+    cfg = capi.synth_cfg(n, dup_mode=1)
+    dev = torch.device("cuda:0")
+    blob_d, offs_d, idx_d, total = engine.synth_corpus_device(cfg, 0, n, dev)
+    blob = blob_d[:total].cpu().numpy()
+    offs = offs_d.cpu().numpy().astype(np.uint64)
+    idx = idx_d.cpu().numpy().astype(np.uint32)
+    cert_id = torch.empty(n, dtype=torch.int64, device=dev)
+    na = torch.empty(n, dtype=torch.int64, device=dev)
+    bc = torch.empty(n, dtype=torch.uint8, device=dev)
+    import ctypes as C
+    assert capi.load().ctmr_synth_truth_device(C.byref(cfg), 0, n, cert_id.data_ptr(), na.data_ptr(), bc.data_ptr(), 1) == 0
+    torch.cuda.synchronize()
+    ids = cert_id.cpu().numpy()
+    del blob_d, offs_d, idx_d, cert_id, na, bc
+    iblob, ioffs = engine.synth_issuers(cfg)
+    devices = list(range(torch.cuda.device_count())) if torch.cuda.device_count() > 1 else [0, 0]
+    with engine.GpuCertGroup(devices, table_capacity=1 << 21, issuer_cn_filter=README_FILTER, max_issuers=1024,
+                             max_batch_entries=16384) as g:
+        r = g.store_batch(blob, offs, iblob, ioffs, idx, NOW_NS)
+        ok = r.status == 0
+        assert 0 < int(r.was_unknown.sum()) * 2 == int(ok.sum())
+        kept = np.nonzero(ok)[0]
+        order = kept[np.argsort(ids[kept], kind="stable")]
+        first_of_pair = np.zeros(n, bool)
+        first_of_pair[order[0::2]] = True           # stable: entry order inside a pair
+        assert np.array_equal(r.was_unknown.astype(bool), first_of_pair)
+        assert sum(g.issuer_counts().values()) == int(r.was_unknown.sum())
+        assert int(g.status_counters()[0]) == int(ok.sum())
+        per = [m.table_stats()[0] for m in g.members]
+        assert sum(per) == int(r.was_unknown.sum()) and min(per) > 0.3 * max(per)   # the owner hash spreads the sets
+        r2 = g.store_batch(blob, offs, iblob, ioffs, idx, NOW_NS, want_sha=False)
+        assert not r2.was_unknown.any() and not r2.first_issuer_hour.any()
+    with engine.GpuCertDatabase(table_capacity=1 << 21, issuer_cn_filter=README_FILTER, max_issuers=1024) as db:
+        s = db.store_batch(blob, offs, iblob, ioffs, idx, NOW_NS)
+    for f in ("status", "sha256", "exp_hour", "was_unknown", "first_issuer_hour"):
+        assert np.array_equal(getattr(r, f), getattr(s, f)), f
