@@ -37,6 +37,7 @@ EXPORTS = [
     "ctmr_group_create", "ctmr_group_destroy", "ctmr_group_last_error", "ctmr_group_size", "ctmr_group_member",
     "ctmr_group_process_batch", "ctmr_group_issuer_counts", "ctmr_group_set_cardinality", "ctmr_group_status_counters",
     "ctmr_group_table_stats", "ctmr_group_preload_known", "ctmr_group_evict_expired", "ctmr_group_reset",
+    "ctmr_group_snapshot_size", "ctmr_group_snapshot_save", "ctmr_group_snapshot_load",
     "ctmr_peer_export", "ctmr_peer_attach", "ctmr_peer_barrier_device", "ctmr_peer_allreduce_histogram_device",
     "ctmr_bind_host_to_device", "ctmr_peer_rounds", "ctmr_peer_round_entries",
 ]
@@ -184,6 +185,9 @@ def load():
     L.ctmr_group_preload_known.argtypes = [vp, i64, vp, vp, vp, u64]
     L.ctmr_group_evict_expired.argtypes = [vp, i64, C.POINTER(u64)]
     L.ctmr_group_reset.argtypes = [vp]
+    L.ctmr_group_snapshot_size.argtypes = [vp, C.POINTER(u64)]
+    L.ctmr_group_snapshot_save.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.ctmr_group_snapshot_load.argtypes = [vp, vp, u64]
     L.ctmr_peer_export.argtypes = [vp, u32, vp]
     L.ctmr_peer_attach.argtypes = [vp, u32, u32, vp]
     L.ctmr_peer_barrier_device.argtypes = [vp, vp]

@@ -1062,6 +1062,73 @@ int ctmr_preload_known(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], 
     return rc;
 }
 
+}  // extern "C"
+
+namespace ctmr_host {
+
+// one shard's tables and histograms, in a fixed order (device <-> host)
+uint64_t snap_shard_bytes(ctmr_ctx* c) {
+    return (c->st.table_mask + 1) * sizeof(KnownSlot) + (c->st.pair_mask + 1) * sizeof(PairSlot) + (c->st.meta_mask + 1) * sizeof(MetaSlot) +
+           c->st.max_issuers * sizeof(uint64_t) + CTMR_ST__COUNT * sizeof(uint64_t);
+}
+
+int snap_shard_save(ctmr_ctx* c, uint8_t* p) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    const uint64_t t = (c->st.table_mask + 1) * sizeof(KnownSlot), pr = (c->st.pair_mask + 1) * sizeof(PairSlot),
+                   m = (c->st.meta_mask + 1) * sizeof(MetaSlot), ic = c->st.max_issuers * sizeof(uint64_t);
+    CU(c, cudaMemcpy(p, c->st.table, t, cudaMemcpyDeviceToHost)); p += t;
+    CU(c, cudaMemcpy(p, c->st.pairs, pr, cudaMemcpyDeviceToHost)); p += pr;
+    CU(c, cudaMemcpy(p, c->st.meta, m, cudaMemcpyDeviceToHost)); p += m;
+    CU(c, cudaMemcpy(p, c->st.issuer_counts, ic, cudaMemcpyDeviceToHost)); p += ic;
+    CU(c, cudaMemcpy(p, c->st.status_counts, CTMR_ST__COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return CTMR_OK;
+}
+
+int snap_shard_load(ctmr_ctx* c, const uint8_t* p) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    const uint64_t t = (c->st.table_mask + 1) * sizeof(KnownSlot), pr = (c->st.pair_mask + 1) * sizeof(PairSlot),
+                   m = (c->st.meta_mask + 1) * sizeof(MetaSlot), ic = c->st.max_issuers * sizeof(uint64_t);
+    CU(c, cudaMemcpy(c->st.table, p, t, cudaMemcpyHostToDevice)); p += t;
+    CU(c, cudaMemcpy(c->st.pairs, p, pr, cudaMemcpyHostToDevice)); p += pr;
+    CU(c, cudaMemcpy(c->st.meta, p, m, cudaMemcpyHostToDevice)); p += m;
+    CU(c, cudaMemcpy(c->st.issuer_counts, p, ic, cudaMemcpyHostToDevice)); p += ic;
+    CU(c, cudaMemcpy(c->st.status_counts, p, CTMR_ST__COUNT * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    // host memos: the DER memo is rebuilt lazily, the digest memos come back from the device registry
+    c->digests.clear();
+    c->issuer_by_digest.clear();
+    c->issuer_by_der.clear();
+    if (c->fe) return fe_clear_issuers(c);
+    return CTMR_OK;
+}
+
+// the device registry (rank 0's region) again, digest i at index i: cleared, then filled by ONE launch of the
+// find-or-insert kernel, which takes a call's digests in order
+int snap_registry_restore(ctmr_ctx* c, const uint8_t* digests, uint64_t n) {
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemsetAsync(c->reg.slots, 0, (c->reg.mask + 1) * sizeof(IssuerRegSlot), c->stream));
+    CU(c, cudaMemsetAsync(c->reg.by_index, 0, (size_t)c->reg.max_issuers * 32, c->stream));
+    CU(c, cudaMemsetAsync(c->reg.counter, 0, sizeof(unsigned long long), c->stream));
+    if (n) {
+        uint8_t* d_dig = nullptr;
+        uint32_t* d_idx = nullptr;
+        CU(c, cudaMalloc(&d_dig, n * 32));
+        CU(c, cudaMalloc(&d_idx, n * sizeof(uint32_t)));
+        CU(c, cudaMemcpyAsync(d_dig, digests, n * 32, cudaMemcpyHostToDevice, c->stream));
+        CU(c, launch_issuer_registry(c->reg, d_dig, nullptr, (uint32_t)n, d_idx, c->st.error_flag, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        cudaFree(d_dig);
+        cudaFree(d_idx);
+    }
+    int rc = refresh_digests(c);
+    if (rc) return rc;
+    if (c->digests.size() != n) return fail(c, CTMR_E_INVALID, "snapshot holds duplicate issuer digests");
+    return ctmr_check_device(c, nullptr);
+}
+
+}  // namespace ctmr_host
+
 namespace {
 struct SnapHeader {
     char magic[8];  // "CTMRSNP3"
@@ -1069,17 +1136,15 @@ struct SnapHeader {
 };
 }  // namespace
 
+extern "C" {
+
 int ctmr_snapshot_size(ctmr_ctx* c, uint64_t* bytes) {
     if (!c || !bytes) return fail(c, CTMR_E_INVALID, "bad argument");
-    if (c->st.peer.world > 1) return fail(c, CTMR_E_INVALID, "snapshots are per single-GPU ctx (a group's shards reference each other's issuer registry)");
+    if (c->st.peer.world > 1) return fail(c, CTMR_E_INVALID, "member of a group: use ctmr_group_snapshot_* (the shards share one issuer registry)");
     CU(c, cudaSetDevice(c->device));
-    {
-        int rc0 = refresh_digests(c);
-        if (rc0) return rc0;
-    }
-    *bytes = sizeof(SnapHeader) + (c->st.table_mask + 1) * sizeof(KnownSlot) + (c->st.pair_mask + 1) * sizeof(PairSlot) +
-             (c->st.meta_mask + 1) * sizeof(MetaSlot) +
-             c->st.max_issuers * sizeof(uint64_t) + CTMR_ST__COUNT * sizeof(uint64_t) + c->digests.size() * 32;
+    int rc = refresh_digests(c);
+    if (rc) return rc;
+    *bytes = sizeof(SnapHeader) + snap_shard_bytes(c) + c->digests.size() * 32;
     return CTMR_OK;
 }
 
@@ -1088,8 +1153,6 @@ int ctmr_snapshot_save(ctmr_ctx* c, uint8_t* buf, uint64_t cap, uint64_t* writte
     int rc = ctmr_snapshot_size(c, &need);
     if (rc) return rc;
     if (!buf || cap < need) return fail(c, CTMR_E_INVALID, "snapshot buffer too small");
-    CU(c, cudaSetDevice(c->device));
-    CU(c, cudaDeviceSynchronize());
     SnapHeader h{};
     std::memcpy(h.magic, "CTMRSNP3", 8);
     h.table_slots = c->st.table_mask + 1;
@@ -1100,11 +1163,9 @@ int ctmr_snapshot_save(ctmr_ctx* c, uint8_t* buf, uint64_t cap, uint64_t* writte
     h.next_index = c->next_index;
     uint8_t* p = buf;
     std::memcpy(p, &h, sizeof h); p += sizeof h;
-    CU(c, cudaMemcpy(p, c->st.table, h.table_slots * sizeof(KnownSlot), cudaMemcpyDeviceToHost)); p += h.table_slots * sizeof(KnownSlot);
-    CU(c, cudaMemcpy(p, c->st.pairs, h.pair_slots * sizeof(PairSlot), cudaMemcpyDeviceToHost)); p += h.pair_slots * sizeof(PairSlot);
-    CU(c, cudaMemcpy(p, c->st.meta, h.meta_slots * sizeof(MetaSlot), cudaMemcpyDeviceToHost)); p += h.meta_slots * sizeof(MetaSlot);
-    CU(c, cudaMemcpy(p, c->st.issuer_counts, h.max_issuers * sizeof(uint64_t), cudaMemcpyDeviceToHost)); p += h.max_issuers * sizeof(uint64_t);
-    CU(c, cudaMemcpy(p, c->st.status_counts, CTMR_ST__COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost)); p += CTMR_ST__COUNT * sizeof(uint64_t);
+    rc = snap_shard_save(c, p);
+    if (rc) return rc;
+    p += snap_shard_bytes(c);
     for (const auto& d : c->digests) { std::memcpy(p, d.data(), 32); p += 32; }
     if (written) *written = (uint64_t)(p - buf);
     return CTMR_OK;
@@ -1118,44 +1179,12 @@ int ctmr_snapshot_load(ctmr_ctx* c, const uint8_t* buf, uint64_t bytes) {
     if (h.table_slots != c->st.table_mask + 1 || h.pair_slots != c->st.pair_mask + 1 || h.meta_slots != c->st.meta_mask + 1 ||
         h.max_issuers != c->st.max_issuers)
         return fail(c, CTMR_E_INVALID, "snapshot was taken with different capacities (table / pairs / max_issuers)");
-    const uint64_t need = sizeof h + h.table_slots * sizeof(KnownSlot) + h.pair_slots * sizeof(PairSlot) +
-                          h.meta_slots * sizeof(MetaSlot) + h.max_issuers * sizeof(uint64_t) + CTMR_ST__COUNT * sizeof(uint64_t) + h.n_issuers * 32;
-    if (bytes < need || h.n_issuers > h.max_issuers) return fail(c, CTMR_E_INVALID, "truncated snapshot");
-    if (c->st.peer.world > 1) return fail(c, CTMR_E_INVALID, "snapshots are per single-GPU ctx");
-    CU(c, cudaSetDevice(c->device));
-    CU(c, cudaDeviceSynchronize());
-    const uint8_t* p = buf + sizeof h;
-    CU(c, cudaMemcpy(c->st.table, p, h.table_slots * sizeof(KnownSlot), cudaMemcpyHostToDevice)); p += h.table_slots * sizeof(KnownSlot);
-    CU(c, cudaMemcpy(c->st.pairs, p, h.pair_slots * sizeof(PairSlot), cudaMemcpyHostToDevice)); p += h.pair_slots * sizeof(PairSlot);
-    CU(c, cudaMemcpy(c->st.meta, p, h.meta_slots * sizeof(MetaSlot), cudaMemcpyHostToDevice)); p += h.meta_slots * sizeof(MetaSlot);
-    CU(c, cudaMemcpy(c->st.issuer_counts, p, h.max_issuers * sizeof(uint64_t), cudaMemcpyHostToDevice)); p += h.max_issuers * sizeof(uint64_t);
-    CU(c, cudaMemcpy(c->st.status_counts, p, CTMR_ST__COUNT * sizeof(uint64_t), cudaMemcpyHostToDevice)); p += CTMR_ST__COUNT * sizeof(uint64_t);
-    c->digests.clear();
-    c->issuer_by_digest.clear();
-    c->issuer_by_der.clear();  // DER memo is rebuilt lazily; dense indices come from the digests
-    if (c->fe) fe_clear_issuers(c);
-    // the device registry again, digest i at index i: cleared, then filled one digest per launch (the counter hands out
-    // the indices in launch order; restores are rare and there are O(thousands) of issuers)
-    CU(c, cudaMemsetAsync(c->reg.slots, 0, (c->reg.mask + 1) * sizeof(IssuerRegSlot), c->stream));
-    CU(c, cudaMemsetAsync(c->reg.by_index, 0, (size_t)c->reg.max_issuers * 32, c->stream));
-    CU(c, cudaMemsetAsync(c->reg.counter, 0, sizeof(unsigned long long), c->stream));
-    if (h.n_issuers) {
-        uint8_t* d_dig = nullptr;
-        uint32_t* d_idx = nullptr;
-        CU(c, cudaMalloc(&d_dig, h.n_issuers * 32));
-        CU(c, cudaMalloc(&d_idx, h.n_issuers * sizeof(uint32_t)));
-        CU(c, cudaMemcpyAsync(d_dig, p, h.n_issuers * 32, cudaMemcpyHostToDevice, c->stream));
-        for (uint64_t i = 0; i < h.n_issuers; ++i)
-            CU(c, launch_issuer_registry(c->reg, d_dig + 32 * i, nullptr, 1, d_idx + i, c->st.error_flag, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        cudaFree(d_dig);
-        cudaFree(d_idx);
-    }
-    c->next_index = h.next_index;
-    int rc = refresh_digests(c);
+    if (bytes < sizeof h + snap_shard_bytes(c) + h.n_issuers * 32 || h.n_issuers > h.max_issuers) return fail(c, CTMR_E_INVALID, "truncated snapshot");
+    if (c->st.peer.world > 1) return fail(c, CTMR_E_INVALID, "member of a group: use ctmr_group_snapshot_*");
+    int rc = snap_shard_load(c, buf + sizeof h);
     if (rc) return rc;
-    if (c->digests.size() != h.n_issuers) return fail(c, CTMR_E_INVALID, "snapshot holds duplicate issuer digests");
-    return ctmr_check_device(c, nullptr);
+    c->next_index = h.next_index;
+    return snap_registry_restore(c, buf + sizeof h + snap_shard_bytes(c), h.n_issuers);
 }
 
 // ------------------------------------------------------------------------------------------------ tooling

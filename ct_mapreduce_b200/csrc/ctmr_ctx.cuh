@@ -242,6 +242,11 @@ int upload_issuer_map(ctmr_ctx* c, const uint32_t* dense, uint32_t n);
 int preload_impl(ctmr_ctx* c, int64_t exp_hour, const uint8_t digest[32], const uint8_t* serial_blob, const uint64_t* serial_offsets,
                  uint64_t n, uint64_t first_index);
 int ensure_stages(ctmr_ctx* c);
+// snapshot pieces (ctmr_api.cu): one shard's tables + histograms, and the registry of the group (rank 0's region)
+uint64_t snap_shard_bytes(ctmr_ctx* c);
+int snap_shard_save(ctmr_ctx* c, uint8_t* p);
+int snap_shard_load(ctmr_ctx* c, const uint8_t* p);
+int snap_registry_restore(ctmr_ctx* c, const uint8_t* digests, uint64_t n);
 int frontend_ensure(ctmr_ctx* c);   // allocates the front end's buffers on first use (ctmr_api.cu)
 int ensure_scratch(ctmr_ctx* c, uint64_t n);
 uint64_t device_round_entries(uint64_t n, uint32_t rounds);   // E of a ctmr_process_device call cut into `rounds` rounds

@@ -620,6 +620,74 @@ int ctmr_group_evict_expired(ctmr_group* g, int64_t now_unix_sec, uint64_t* evic
     return CTMR_OK;
 }
 
+// Snapshot of a whole group: every shard's tables and histograms + the one issuer registry + the group's next index.
+namespace {
+struct GroupSnapHeader {
+    char magic[8];  // "CTMRGRP1"
+    uint64_t members, shard_bytes, table_slots, max_issuers, n_issuers, next_index;
+};
+}  // namespace
+
+int ctmr_group_snapshot_size(ctmr_group* g, uint64_t* bytes) {
+    if (!g || g->m.empty() || !bytes) return CTMR_E_INVALID;
+    ctmr_ctx* c0 = g->m[0];
+    cudaSetDevice(c0->device);
+    const int rc = refresh_digests(c0);
+    if (rc) return group_fail(g, c0, rc);
+    *bytes = sizeof(GroupSnapHeader) + g->m.size() * snap_shard_bytes(c0) + c0->digests.size() * 32;
+    return CTMR_OK;
+}
+
+int ctmr_group_snapshot_save(ctmr_group* g, uint8_t* buf, uint64_t cap, uint64_t* written) {
+    uint64_t need = 0;
+    int rc = ctmr_group_snapshot_size(g, &need);
+    if (rc) return rc;
+    ctmr_ctx* c0 = g->m[0];
+    if (!buf || cap < need) return group_fail(g, c0, fail(c0, CTMR_E_INVALID, "snapshot buffer too small"));
+    GroupSnapHeader h{};
+    std::memcpy(h.magic, "CTMRGRP1", 8);
+    h.members = g->m.size();
+    h.shard_bytes = snap_shard_bytes(c0);
+    h.table_slots = c0->st.table_mask + 1;
+    h.max_issuers = c0->st.max_issuers;
+    h.n_issuers = c0->digests.size();
+    h.next_index = g->next_index;
+    uint8_t* p = buf;
+    std::memcpy(p, &h, sizeof h); p += sizeof h;
+    for (ctmr_ctx* c : g->m) {
+        rc = snap_shard_save(c, p);
+        if (rc) return group_fail(g, c, rc);
+        p += h.shard_bytes;
+    }
+    for (const auto& d : c0->digests) { std::memcpy(p, d.data(), 32); p += 32; }
+    if (written) *written = (uint64_t)(p - buf);
+    return CTMR_OK;
+}
+
+int ctmr_group_snapshot_load(ctmr_group* g, const uint8_t* buf, uint64_t bytes) {
+    if (!g || g->m.empty()) return CTMR_E_INVALID;
+    ctmr_ctx* c0 = g->m[0];
+    GroupSnapHeader h;
+    if (!buf || bytes < sizeof h) return group_fail(g, c0, fail(c0, CTMR_E_INVALID, "bad snapshot"));
+    std::memcpy(&h, buf, sizeof h);
+    if (std::memcmp(h.magic, "CTMRGRP1", 8) != 0) return group_fail(g, c0, fail(c0, CTMR_E_INVALID, "not a ctmr group snapshot"));
+    // the owner of a set depends on the group size: a snapshot only fits a group of the same shape
+    if (h.members != g->m.size() || h.shard_bytes != snap_shard_bytes(c0) || h.table_slots != c0->st.table_mask + 1 ||
+        h.max_issuers != c0->st.max_issuers || h.n_issuers > h.max_issuers)
+        return group_fail(g, c0, fail(c0, CTMR_E_INVALID, "snapshot was taken by a group of another size or with other capacities"));
+    if (bytes < sizeof h + h.members * h.shard_bytes + h.n_issuers * 32) return group_fail(g, c0, fail(c0, CTMR_E_INVALID, "truncated snapshot"));
+    const uint8_t* p = buf + sizeof h;
+    for (ctmr_ctx* c : g->m) {
+        const int rc = snap_shard_load(c, p);
+        if (rc) return group_fail(g, c, rc);
+        p += h.shard_bytes;
+    }
+    const int rc = snap_registry_restore(c0, p, h.n_issuers);
+    if (rc) return group_fail(g, c0, rc);
+    g->next_index = h.next_index;
+    return CTMR_OK;
+}
+
 int ctmr_group_reset(ctmr_group* g) {
     if (!g || g->m.empty()) return CTMR_E_INVALID;
     for (ctmr_ctx* c : g->m) {

@@ -409,6 +409,18 @@ class GpuCertGroup(GpuCertDatabase):
     def reset(self):
         self._check(self._lib.ctmr_group_reset(self._h))
 
+    def snapshot(self) -> np.ndarray:
+        need = C.c_uint64(0)
+        self._check(self._lib.ctmr_group_snapshot_size(self._h, C.byref(need)))
+        buf = np.empty(need.value, np.uint8)
+        wrote = C.c_uint64(0)
+        self._check(self._lib.ctmr_group_snapshot_save(self._h, capi.ptr(buf), buf.size, C.byref(wrote)))
+        return buf[:wrote.value]
+
+    def restore(self, snap: np.ndarray):
+        snap = np.ascontiguousarray(snap, np.uint8)
+        self._check(self._lib.ctmr_group_snapshot_load(self._h, capi.ptr(snap), snap.size))
+
     def get_known_certificates(self, exp_hour: int, issuer_digest: bytes):
         grp = self
 
@@ -444,7 +456,7 @@ class GpuCertGroup(GpuCertDatabase):
     # the device-resident / per-ctx entry points of the base class do not take a group handle
     map_device = reduce_device = process_device = read_histogram_device = profile_last = sha256_ceiling = _single_ctx_only
     reset_device = check_device = peer_export = peer_attach = peer_barrier_device = _single_ctx_only
-    peer_allreduce_histogram_device = snapshot = restore = frontend_profile_last = _single_ctx_only
+    peer_allreduce_histogram_device = frontend_profile_last = _single_ctx_only
 
 
 # ---------------------------------------------------------------------- synthetic corpus (bench/test tooling)

@@ -349,23 +349,35 @@ func (d *DB) EvictExpired(nowUnixSec int64) (uint64, error) {
 	return uint64(n), d.err(rc, "ctmr_evict_expired")
 }
 
-// Snapshot / Restore of a single-GPU ctx's derived state (groups rebuild from Redis with PreloadKnown).
+// Snapshot / Restore of the derived device state: one ctx, or every shard of a group plus its one issuer registry.
+// A snapshot restores into a DB of the same shape (capacities; for a group also the number of shards, because the
+// owner of a set depends on it).  The []byte is only read / written during the call (cgo pins it).
 func (d *DB) Snapshot() ([]byte, error) {
-	if d.h == nil {
-		return nil, fmt.Errorf("snapshots are per single-GPU ctx")
-	}
 	var need, wrote C.uint64_t
-	if err := d.err(C.ctmr_snapshot_size(d.h, &need), "ctmr_snapshot_size"); err != nil {
+	var rc C.int
+	if d.g != nil {
+		rc = C.ctmr_group_snapshot_size(d.g, &need)
+	} else {
+		rc = C.ctmr_snapshot_size(d.h, &need)
+	}
+	if err := d.err(rc, "ctmr_snapshot_size"); err != nil {
 		return nil, err
 	}
 	buf := make([]byte, int(need))
-	rc := C.ctmr_snapshot_save(d.h, (*C.uint8_t)(unsafe.Pointer(&buf[0])), need, &wrote)
+	if d.g != nil {
+		rc = C.ctmr_group_snapshot_save(d.g, (*C.uint8_t)(unsafe.Pointer(&buf[0])), need, &wrote)
+	} else {
+		rc = C.ctmr_snapshot_save(d.h, (*C.uint8_t)(unsafe.Pointer(&buf[0])), need, &wrote)
+	}
 	return buf[:int(wrote)], d.err(rc, "ctmr_snapshot_save")
 }
 
 func (d *DB) Restore(snap []byte) error {
-	if d.h == nil {
-		return fmt.Errorf("snapshots are per single-GPU ctx")
+	if len(snap) == 0 {
+		return fmt.Errorf("empty snapshot")
+	}
+	if d.g != nil {
+		return d.err(C.ctmr_group_snapshot_load(d.g, (*C.uint8_t)(unsafe.Pointer(&snap[0])), C.uint64_t(len(snap))), "ctmr_group_snapshot_load")
 	}
 	return d.err(C.ctmr_snapshot_load(d.h, (*C.uint8_t)(unsafe.Pointer(&snap[0])), C.uint64_t(len(snap))), "ctmr_snapshot_load")
 }

@@ -286,6 +286,11 @@ int ctmr_group_preload_known(ctmr_group* g, int64_t exp_hour, const uint8_t issu
                              const uint64_t* serial_offsets, uint64_t n);
 int ctmr_group_evict_expired(ctmr_group* g, int64_t now_unix_sec, uint64_t* evicted_out);
 int ctmr_group_reset(ctmr_group* g);
+/* snapshot of the whole group (every shard + the one issuer registry); restores into a group of the same size and
+ * capacities (a set's owner depends on the group size) */
+int ctmr_group_snapshot_size(ctmr_group* g, uint64_t* bytes);
+int ctmr_group_snapshot_save(ctmr_group* g, uint8_t* buf, uint64_t cap, uint64_t* written);
+int ctmr_group_snapshot_load(ctmr_group* g, const uint8_t* buf, uint64_t bytes);
 
 /* ---- several GPUs, one PROCESS PER GPU (torchrun-style launches) ------------------------------ */
 /* Every rank creates its ctx with the same capacities, exports a handle, gathers all handles by whatever means the

@@ -186,6 +186,53 @@ def test_group_issuer_registry_is_order_independent(eng, ora):
         _check_fields(got, want, n, FIELDS)
 
 
+def test_group_snapshot_and_restore(eng, ora):
+    """Checkpoint / resume of the multi-shard form: every shard's tables + the one issuer registry +
+    the group's next index, restored into a NEW group of the same shape; the second half then behaves as if the first
+    had run there.  A group of another size (the owner of a set would change) and a member ctx are refused."""
+    from ct_mapreduce_b200 import capi
+    n = 12000
+    cfg = ora.synth_cfg(n, len_mode=1, len_lo=512, len_hi=4096, dup_mode=1)
+    blob, offs, idx = ora.synth_corpus(cfg, 0, n)
+    iblob, ioffs = ora.synth_issuers(cfg)
+    h = n // 2
+    odb = ora.DB(README_FILTER, False)
+    wa = odb.process(blob, offs[:h + 1], iblob, ioffs, idx[:h], NOW_NS)
+    wb = odb.process(blob, offs[h:], iblob, ioffs, idx[h:], NOW_NS)
+    kw = dict(table_capacity=1 << 15, issuer_cn_filter=README_FILTER, max_issuers=1024, max_batch_entries=1024, pair_capacity_log2=15)
+    for devices in _device_sets():
+        with eng.GpuCertGroup(devices, **kw) as g1:
+            # register in reverse first: the restored registry must reproduce THESE indices, not first-seen order
+            ni = ioffs.size - 1
+            ders = [iblob[ioffs[k]:ioffs[k + 1]].tobytes() for k in range(ni)][::-1]
+            ro = np.zeros(ni + 1, np.uint64)
+            ro[1:] = np.cumsum([len(d) for d in ders], dtype=np.uint64)
+            g1.register_issuers(np.frombuffer(b"".join(ders), np.uint8), ro)
+            dense1 = g1.register_issuers(iblob, ioffs)
+            ga = g1.store_batch(blob, offs[:h + 1], iblob, ioffs, idx[:h], NOW_NS, want_meta=True)
+            _check_fields(ga, wa, h, FIELDS + META)
+            snap = g1.snapshot().copy()
+            with pytest.raises(capi.CtmrError):
+                g1.members[0].snapshot()          # a shard alone is not a consistent checkpoint
+        with eng.GpuCertGroup(devices, **kw) as g2:
+            g2.restore(snap)
+            assert np.array_equal(g2.register_issuers(iblob, ioffs), dense1)
+            gb = g2.store_batch(blob, offs[h:], iblob, ioffs, idx[h:], NOW_NS, want_meta=True)
+            _check_fields(gb, wb, n - h, FIELDS + META)
+            assert {k: v for k, v in g2.issuer_counts().items() if v} == odb.issuer_counts()
+            assert np.array_equal(g2.status_counters(), odb.filter_counters())
+            assert np.array_equal(g2.snapshot(), g2.snapshot())
+        other = list(devices) + [devices[0]] if len(devices) < 8 else list(devices)[:-1]
+        with eng.GpuCertGroup(other, **kw) as g3:
+            with pytest.raises(capi.CtmrError):
+                g3.restore(snap)
+        with eng.GpuCertGroup(devices, **dict(kw, table_capacity=1 << 14)) as g4:
+            with pytest.raises(capi.CtmrError):
+                g4.restore(snap)
+            with pytest.raises(capi.CtmrError):
+                g4.restore(snap[:100])
+
+
 # ------------------------------------------------------------------------------------------------ one process per GPU
 def _free_port():
     s = socket.socket()
