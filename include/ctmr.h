@@ -148,7 +148,10 @@ uint32_t ctmr_issuer_count(ctmr_ctx* ctx);
  * back to back (entry i = blob[offsets[i] .. offsets[i+1])); issuer_* hold the batch's distinct
  * Chain[0] certificates and issuer_idx[i] selects one (CTMR_ISSUER_NONE = no chain).
  * now_unix_ns replaces time.Now() at ct-fetch.go:52.  Copies host->device, runs the kernels,
- * copies the requested outputs back; synchronous. */
+ * copies the requested outputs back; synchronous.
+ * After a failure (rc != 0) the outputs are undefined and part of the batch may already be in the tables; the
+ * call's entry indices are consumed either way, so replaying the batch is safe in the reference's own sense
+ * (idempotent replays): entries that were inserted read as known, never as unknown twice. */
 int ctmr_process_batch(ctmr_ctx* ctx, const uint8_t* blob, const uint64_t* offsets /* [n+1] */, uint64_t n,
                        const uint8_t* issuer_blob, const uint64_t* issuer_offsets /* [n_issuers+1] */,
                        uint32_t n_issuers, const uint32_t* issuer_idx /* [n] */, int64_t now_unix_ns,
